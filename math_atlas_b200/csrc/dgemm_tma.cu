@@ -1,0 +1,276 @@
+// DGEMM fast path for sm_100a: TMA-fed, mbarrier-pipelined, FP64 tensor-core (DMMA) kernel.
+//
+// Replaces the hot loop of the reference's access-major GEMM:
+//   iploopsK + ammkern_t + cm2am_t copies  (AtlasBase/Clint/atlas-ammm.base:29602, :577, :544-570)
+// ATLAS copies A/B into "access-major" blocks (transpose folded into the copy) and then runs a
+// register-blocked kernel on them.  Here the copy *is* the TMA load: the tensor map describes the
+// matrix as stored (so NoTrans/Trans only decide which of two box shapes is used), the 128-byte
+// TMA swizzle is the bank-conflict-free "access-major" order, and the micro-kernel is
+// mma.sync.m8n8k4.f64 (the only FP64 tensor shape sm_100a has natively: every larger f64 mma
+// shape lowers to DMMA.8x8x4 in SASS; tcgen05 has no f64 kind).
+//
+// Tile: 128x128x16 per stage, 8 consumer warps (64x32 each, 8x4 DMMA tiles -> 64 fp64
+// accumulators/thread) + 1 TMA producer warp, 6-stage ring (192 KB smem), one CTA per SM.
+//
+// K-slot permutation.  DMMA needs a(row g, kslot t) and b(kslot t, col g) with g=lane>>2,
+// t=lane&3.  Any bijection kslot->k inside the 16-deep stage is legal as long as A and B agree;
+//   k(j,t) = (12*(t>>1) + 3*(t&1)) ^ (4*(j>>1) + (j&1)),   j = 0..3 (the four k4 groups)
+// makes every 64-bit fragment load conflict-free in BOTH swizzled layouts:
+//   K-major tile  [row r][16 k]   (A^T, B):   8B position = (((k>>1) ^ (r&7))<<1) | (k&1)
+//   MN-major tile [k][16 m] per 16-row group (A, B^T): position = ((((m&15)>>1) ^ (k&7))<<1) | (m&1)
+#include "common.cuh"
+#include "dgemm_tma.h"
+#include <cuda.h>
+#include <mutex>
+
+namespace ab {
+
+namespace {
+
+constexpr int BM = 128, BN = 128, BK = 16, STAGES = 6;
+constexpr int A_TILE_BYTES = BM * BK * 8, B_TILE_BYTES = BN * BK * 8;
+constexpr int STAGE_BYTES = A_TILE_BYTES + B_TILE_BYTES;
+constexpr int CONS_WARPS = 8, THREADS = (CONS_WARPS + 1) * 32;
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 2 * STAGES * 8;
+constexpr int GROUP_M = 16;  // tile rasterisation group (L2 reuse of the B panel)
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint32_t a, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(a), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t a, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(a), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t a) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(a) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t a, uint32_t parity) {
+  uint32_t done;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done) : "r"(a), "r"(parity) : "memory");
+  } while (!done);
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* tm, int c0, int c1, uint32_t mbar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tm)), "r"(c0), "r"(c1), "r"(mbar) : "memory");
+}
+__device__ __forceinline__ double lds_f64(uint32_t a) {
+  double v;
+  asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
+  asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+               : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
+
+// compile-time XOR terms of the fragment addresses (see header comment)
+__host__ __device__ constexpr uint32_t jmask(int j) { return (uint32_t)(((j >> 1) << 2) | (j & 1)); }
+// K-major: bits 5 and 3
+__host__ __device__ constexpr uint32_t xk(int j) { return (uint32_t)(((j >> 1) << 5) | ((j & 1) << 3)); }
+// MN-major: k*128 term and chunk term; hi8 = ((row block index)&1) i.e. (mb & 8) != 0
+__host__ __device__ constexpr uint32_t xm(int j, int hi8) {
+  return (jmask(j) << 7) ^ ((((uint32_t)hi8 << 2) ^ jmask(j)) << 4);
+}
+
+template <bool A_KMAJOR, bool B_KMAJOR>
+__global__ void __launch_bounds__(THREADS, 1)
+dgemm_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                 double* __restrict__ C, size_t ldc, int M, int N, int K, double alpha, double beta,
+                 int cmode, int tiles_m, int tiles_n) {
+  // ---- tile coordinates (grouped rasterisation) ----
+  const int pid = blockIdx.x;
+  const int in_group = GROUP_M * tiles_n;
+  const int first_m = (pid / in_group) * GROUP_M;
+  const int gsz = min(tiles_m - first_m, GROUP_M);
+  const int tile_m = first_m + (pid % in_group) % gsz;
+  const int tile_n = (pid % in_group) / gsz;
+  const int m0 = tile_m * BM, n0 = tile_n * BN;
+  if (cmode == C_UPPER && m0 > n0 + BN - 1) return;
+  if (cmode == C_LOWER && n0 > m0 + BM - 1) return;
+
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t bar_base = smem_base + STAGES * STAGE_BYTES;  // full[s] at +8s, empty[s] at +8(STAGES+s)
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; s++) {
+      mbar_init(bar_base + 8 * s, 1);
+      mbar_init(bar_base + 8 * (STAGES + s), CONS_WARPS);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+
+  const int KT = (K + BK - 1) / BK;
+
+  if (warp == CONS_WARPS) {
+    // ===================== TMA producer warp =====================
+    for (int kt = 0; kt < KT; kt++) {
+      const int s = kt % STAGES;
+      const uint32_t ph = (kt / STAGES) & 1;
+      mbar_wait(bar_base + 8 * (STAGES + s), ph ^ 1);
+      const uint32_t full = bar_base + 8 * s;
+      const uint32_t sa = smem_base + s * STAGE_BYTES, sb = sa + A_TILE_BYTES;
+      const int k0 = kt * BK;
+      if (lane == 0) mbar_expect_tx(full, STAGE_BYTES);
+      __syncwarp();
+      if (A_KMAJOR) { if (lane == 0) tma_load_2d(sa, &tmA, k0, m0, full); }
+      else          { if (lane < 8) tma_load_2d(sa + lane * 2048, &tmA, m0 + 16 * lane, k0, full); }
+      if (B_KMAJOR) { if (lane == 16) tma_load_2d(sb, &tmB, k0, n0, full); }
+      else          { if (lane >= 16 && lane < 24) tma_load_2d(sb + (lane - 16) * 2048, &tmB, n0 + 16 * (lane - 16), k0, full); }
+    }
+    return;
+  }
+
+  // ===================== DMMA consumer warps =====================
+  const int g = lane >> 2, t = lane & 3;
+  const int wm = warp & 1, wn = warp >> 1;            // 2 x 4 warps -> 64 x 32 warp tiles
+  const uint32_t base_t = (uint32_t)((t >> 1) * 12 + (t & 1) * 3);
+  // lane-constant parts of the fragment offsets
+  const uint32_t LK = (uint32_t)g * 128u + ((((base_t >> 1) ^ (uint32_t)g) & 7u) << 4) + ((base_t & 1u) << 3);
+  const uint32_t LM = base_t * 128u + (((((uint32_t)g >> 1) ^ (base_t & 7u)) & 7u) << 4) + (((uint32_t)g & 1u) << 3);
+  const uint32_t a_lane = A_KMAJOR ? (uint32_t)(wm * 64) * 128u + LK : (uint32_t)(wm * 4) * 2048u + LM;
+  const uint32_t b_lane = B_KMAJOR ? (uint32_t)(wn * 32) * 128u + LK : (uint32_t)(wn * 2) * 2048u + LM;
+
+  double acc[8][4][2];
+#pragma unroll
+  for (int i = 0; i < 8; i++)
+#pragma unroll
+    for (int j = 0; j < 4; j++) { acc[i][j][0] = 0.; acc[i][j][1] = 0.; }
+
+  for (int kt = 0; kt < KT; kt++) {
+    const int s = kt % STAGES;
+    const uint32_t ph = (kt / STAGES) & 1;
+    mbar_wait(bar_base + 8 * s, ph);
+    const uint32_t sa = smem_base + s * STAGE_BYTES, sb = sa + A_TILE_BYTES;
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+      double a[8], b[4];
+#pragma unroll
+      for (int mi = 0; mi < 8; mi++) {
+        // K-major: rows advance 8*128 B per mi; MN-major: 16-row group = 2048 B, (mi&1) picks the half
+        const uint32_t off = A_KMAJOR ? ((a_lane + mi * 1024u) ^ xk(j))
+                                      : (a_lane + (mi >> 1) * 2048u) ^ xm(j, mi & 1);
+        a[mi] = lds_f64(sa + off);
+      }
+#pragma unroll
+      for (int ni = 0; ni < 4; ni++) {
+        const uint32_t off = B_KMAJOR ? ((b_lane + ni * 1024u) ^ xk(j))
+                                      : (b_lane + (ni >> 1) * 2048u) ^ xm(j, ni & 1);
+        b[ni] = lds_f64(sb + off);
+      }
+#pragma unroll
+      for (int mi = 0; mi < 8; mi++)
+#pragma unroll
+        for (int ni = 0; ni < 4; ni++) dmma884(acc[mi][ni][0], acc[mi][ni][1], a[mi], b[ni]);
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(bar_base + 8 * (STAGES + s));
+  }
+
+  // ---- epilogue: C = alpha*acc + beta*C (ablk2cmat, atlas-ammm.base:550), triangle mask for SYRK ----
+  const bool beta0 = (beta == 0.);
+#pragma unroll
+  for (int ni = 0; ni < 4; ni++) {
+#pragma unroll
+    for (int e = 0; e < 2; e++) {
+      const int n = n0 + wn * 32 + ni * 8 + 2 * t + e;
+      if (n >= N) continue;
+      double* cc = C + (size_t)n * ldc;
+#pragma unroll
+      for (int mi = 0; mi < 8; mi++) {
+        const int m = m0 + wm * 64 + mi * 8 + g;
+        if (m >= M) continue;
+        if (cmode == C_UPPER && m > n) continue;
+        if (cmode == C_LOWER && m < n) continue;
+        double r = alpha * acc[mi][ni][e];
+        if (!beta0) r += beta * cc[m];
+        cc[m] = r;
+      }
+    }
+  }
+}
+
+// ---------------- host side: tensor-map encode through the driver entry point ----------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    AB_CUDA_CHECK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q));
+    if (!p || q != cudaDriverEntryPointSuccess) { fprintf(stderr, "atlas_b200: cuTensorMapEncodeTiled unavailable\n"); abort(); }
+    fn = reinterpret_cast<EncodeTiledFn>(p);
+  });
+  return fn;
+}
+
+// Stored column-major matrix rows x cols (ld): dim0 = rows (contiguous), dim1 = cols.
+bool make_map(CUtensorMap* tm, const double* ptr, size_t rows, size_t cols, size_t ld, int box0, int box1) {
+  cuuint64_t dims[2] = {(cuuint64_t)rows, (cuuint64_t)cols};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * 8};
+  cuuint32_t box[2] = {(cuuint32_t)box0, (cuuint32_t)box1};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = get_encode()(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, const_cast<double*>(ptr), dims, strides, box, estr,
+                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                            CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS;
+}
+
+template <bool AK, bool BK_>
+void launch(const CUtensorMap& ta, const CUtensorMap& tb, double* C, size_t ldc, int M, int N, int K, double alpha,
+            double beta, int cmode) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    AB_CUDA_CHECK(cudaFuncSetAttribute(dgemm_tma_kernel<AK, BK_>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    attr_set = true;
+  }
+  const int tiles_m = (M + BM - 1) / BM, tiles_n = (N + BN - 1) / BN;
+  dgemm_tma_kernel<AK, BK_><<<tiles_m * tiles_n, THREADS, SMEM_BYTES, current_stream()>>>(
+      ta, tb, C, ldc, M, N, K, alpha, beta, cmode, tiles_m, tiles_n);
+  count_launch();
+  AB_CUDA_CHECK(cudaGetLastError());
+}
+
+}  // namespace
+
+bool dgemm_tma_eligible(int M, int N, int K, const double* A, size_t lda, const double* B, size_t ldb) {
+  // TMA needs 16-byte aligned base and row pitch (global stride multiple of 16 B => even ld).
+  if (M <= 0 || N <= 0 || K <= 0) return false;
+  if ((reinterpret_cast<uintptr_t>(A) & 15) || (reinterpret_cast<uintptr_t>(B) & 15)) return false;
+  if ((lda & 1) || (ldb & 1)) return false;
+  if ((long long)((M + BM - 1) / BM) * ((N + BN - 1) / BN) > 0x7fffffffLL) return false;
+  return true;
+}
+
+bool dgemm_tma(int ta, int tb, int M, int N, int K, double alpha, const double* A, size_t lda, const double* B,
+               size_t ldb, double beta, double* C, size_t ldc, int cmode) {
+  if (!dgemm_tma_eligible(M, N, K, A, lda, B, ldb)) return false;
+  CUtensorMap mA, mB;
+  bool ok;
+  // op(A) is M x K.  ta: stored K x M (k contiguous, K-major) else stored M x K (m contiguous).
+  ok = ta ? make_map(&mA, A, K, M, lda, BK, BM) : make_map(&mA, A, M, K, lda, 16, BK);
+  if (!ok) return false;
+  // op(B) is K x N.  !tb: stored K x N (K-major) else stored N x K (n contiguous).
+  ok = tb ? make_map(&mB, B, N, K, ldb, 16, BK) : make_map(&mB, B, K, N, ldb, BK, BN);
+  if (!ok) return false;
+  if (ta) { if (!tb) launch<true, true>(mA, mB, C, ldc, M, N, K, alpha, beta, cmode);
+            else     launch<true, false>(mA, mB, C, ldc, M, N, K, alpha, beta, cmode); }
+  else    { if (!tb) launch<false, true>(mA, mB, C, ldc, M, N, K, alpha, beta, cmode);
+            else     launch<false, false>(mA, mB, C, ldc, M, N, K, alpha, beta, cmode); }
+  return true;
+}
+
+}  // namespace ab

@@ -1,0 +1,11 @@
+// Fast DGEMM path (TMA + DMMA).  See dgemm_tma.cu.
+#pragma once
+#include <cstddef>
+namespace ab {
+// true if the TMA path can take this problem (16-byte aligned bases, even leading dimensions).
+bool dgemm_tma_eligible(int M, int N, int K, const double* A, size_t lda, const double* B, size_t ldb);
+// C(cmode triangle) = alpha*op(A)*op(B) + beta*C on device pointers; ta/tb = 1 for transposed operands.
+// Returns false (nothing launched) when not eligible.
+bool dgemm_tma(int ta, int tb, int M, int N, int K, double alpha, const double* A, size_t lda, const double* B,
+               size_t ldb, double beta, double* C, size_t ldc, int cmode);
+}  // namespace ab
