@@ -1,0 +1,60 @@
+#!/bin/bash
+# ORACLE recipe: build oracle/_ref/libatlref.so from the reference's own C sources, read where
+# they lie under /root/reference.  Nothing from the reference is copied into the repository:
+# the extracted tree lives in a scratch directory under oracle/_ref/ (git-ignored) and is deleted
+# once the shared library is linked.
+#
+# What is (and is not) the reference here:
+#  * The reference ships "basefiles"; extract.c (its macro pre-processor) expands them into plain
+#    C.  We run that expansion for the handful of directories on the hot path only.
+#  * We do NOT run the reference's configure / empirical-search build (it needs > 1 h, generated
+#    kernels and tuned headers): the tuned amm GEMM is therefore "unbuildable" by the rules of
+#    this repo.  What IS built is the code the reference itself trusts in its
+#    testers: the reference BLAS ATL_Xref* (Antoine/atlrefblas.base), the tester generators /
+#    norms (Clint/atlas-tst.base) and the real recursive LAPACK drivers ATL_getrfC / ATL_getf2 /
+#    ATL_laswp / ATL_potrf{L,U} (Clint/atlas-lp.base) linked against that reference BLAS through
+#    oracle/ref_shim/cblas_to_ref.c (our glue: cblas_* -> ATL_Xref*).
+#  * oracle/ref_shim/*.h are ours: the few configure-probed facts (type sizes, IEEE limits,
+#    L1 size) the sources need.
+set -euo pipefail
+REF=${REF:-/root/reference}
+HERE=$(cd "$(dirname "$0")" && pwd)
+OUT=$HERE/_ref
+W=$OUT/work
+if [ ! -f "$REF/extract.c" ]; then
+  echo "build_ref: $REF not present (GPU box?) - keeping prebuilt $OUT/libatlref.so if any"; exit 0
+fi
+rm -rf "$W"; mkdir -p "$W"; cd "$W"
+gcc -O2 -w -o xextract "$REF/extract.c" 2>/dev/null
+./xextract -langM -b "$REF/AtlasBase/make.base" -o Makefile rout=Make.atldir \
+    -def topd "$REF/AtlasBase" -def ext "$W/xextract" > /dev/null 2>&1
+make ATLAS ATLAS/include ATLAS/src ATLAS/src/testing ATLAS/src/lapack ATLAS/src/blas ATLAS/src/auxil \
+     ATLAS/src/blas/reference ATLAS/src/blas/reference/level1 ATLAS/src/blas/reference/level2 \
+     ATLAS/src/blas/reference/level3 > extract.log 2>&1
+A=$W/ATLAS
+CF="-O2 -ffp-contract=off -fPIC -w -DATL_NoF77 -I$HERE/ref_shim -I$A/include"
+mkdir -p obj
+# 1. reference BLAS (type is in the file name)
+ls $A/src/blas/reference/level1/*.c $A/src/blas/reference/level2/*.c $A/src/blas/reference/level3/*.c | \
+  xargs -P 8 -I{} sh -c 'gcc '"$CF"' -c {} -o obj/$(basename {} .c).o'
+# 2. per-type tester generators / norms, LAPACK drivers and the few aux routines they call
+for t in s:SREAL d:DREAL c:SCPLX z:DCPLX; do
+  p=${t%%:*}; D=${t##*:}
+  for f in testing/ATL_gegen testing/ATL_epsilon testing/ATL_genrm1 testing/ATL_gediffnrm1 testing/ATL_synrm \
+           testing/ATL_trnrm1 lapack/ATL_getrf lapack/ATL_getrfC lapack/ATL_getrfR lapack/ATL_getf2 lapack/ATL_laswp \
+           lapack/ATL_potrf lapack/ATL_potrfL lapack/ATL_potrfU; do
+    gcc $CF -D$D -c $A/src/$f.c -o obj/${p}_$(basename $f).o
+  done
+  if [ $p = c ] || [ $p = z ]; then
+    for f in testing/ATL_henrm lapack/ATL_potrfRL lapack/ATL_potrfRU auxil/ATL_cplxinvert auxil/ATL_cplxdivide; do
+      gcc $CF -D$D -c $A/src/$f.c -o obj/${p}_$(basename $f).o
+    done
+  fi
+  gcc $CF -D$D -c $HERE/ref_shim/cblas_to_ref.c -o obj/${p}_cblas_to_ref.o
+done
+gcc $CF -DDREAL -c $A/src/testing/ATL_rand.c -o obj/ATL_rand.o
+gcc $CF -DSCPLX -c $A/src/lapack/ATL_lapy2.c -o obj/c_lapy2.o
+gcc $CF -DDCPLX -c $A/src/lapack/ATL_lapy2.c -o obj/z_lapy2.o
+gcc -shared -o "$OUT/libatlref.so" obj/*.o -lm
+cd "$HERE"; rm -rf "$W"
+echo "build_ref: built $OUT/libatlref.so"

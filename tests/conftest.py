@@ -1,0 +1,30 @@
+import os
+import sys
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+
+
+@pytest.fixture(scope="session")
+def orc():
+    from oracle import orc as m
+    return m
+
+
+@pytest.fixture(scope="session")
+def oracle(orc):
+    return orc.Oracle()
+
+
+@pytest.fixture(scope="session")
+def ref(orc):
+    try:
+        return orc.Ref()
+    except (FileNotFoundError, OSError) as e:
+        pytest.skip(f"oracle/_ref not available: {e}")
