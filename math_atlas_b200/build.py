@@ -1,0 +1,56 @@
+"""Build libatlas_b200.so (the C-ABI shared library) in-tree with nvcc for sm_100a.
+
+    python -m math_atlas_b200.build            # or: from math_atlas_b200.build import build; build()
+
+nvcc cross-compiles without a GPU.  cudart is linked statically so the library has no
+dependency on the CUDA runtime PyTorch ships.
+"""
+import os
+import subprocess
+import sys
+from concurrent.futures import ThreadPoolExecutor
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+OBJ = os.path.join(CSRC, "obj")
+LIB = os.path.join(HERE, "libatlas_b200.so")
+SOURCES = ["runtime.cu", "dgemm_tma.cu", "level3.cu", "lapack.cu", "capi.cu"]
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC",
+              "--expt-relaxed-constexpr", "-diag-suppress", "177,550"]
+
+
+def _needs(obj, deps):
+    return (not os.path.exists(obj)) or any(os.path.getmtime(d) > os.path.getmtime(obj) for d in deps)
+
+
+def build(force=False, verbose=False):
+    os.makedirs(OBJ, exist_ok=True)
+    headers = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".h", ".cuh"))]
+    nvcc = os.environ.get("NVCC", "nvcc")
+
+    def one(src):
+        s = os.path.join(CSRC, src)
+        o = os.path.join(OBJ, src.replace(".cu", ".o"))
+        if force or _needs(o, [s] + headers):
+            cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", s, "-o", o]
+            r = subprocess.run(cmd, capture_output=True, text=True)
+            if r.returncode != 0:
+                raise RuntimeError(f"nvcc failed for {src}:\n{r.stdout}\n{r.stderr}")
+            if verbose:
+                sys.stderr.write(r.stderr)
+            return o, True
+        return o, False
+
+    with ThreadPoolExecutor(max_workers=len(SOURCES)) as ex:
+        res = list(ex.map(one, SOURCES))
+    objs = [o for o, _ in res]
+    if force or any(c for _, c in res) or not os.path.exists(LIB):
+        cmd = [nvcc, "-shared", "-cudart", "static", "-o", LIB] + objs + ["-Xlinker", "--no-undefined", "-lpthread", "-ldl", "-lrt"]
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
+    return LIB
+
+
+if __name__ == "__main__":
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

@@ -1,0 +1,57 @@
+// Device-level (all pointers are device pointers, work is enqueued on ab::current_stream(),
+// nothing synchronises) level-3 BLAS and LAPACK drivers.  The C ABI in capi.cu wraps these with
+// argument checking, host<->device staging and the final stream synchronisation.
+// T is float, double, float2 (c) or double2 (z).  Enum values are the CBLAS ones (common.cuh).
+#pragma once
+#include "common.cuh"
+
+namespace ab {
+
+// C <- alpha*op(A)*op(B) + beta*C         (reference ATL_Xgemm, Clint/atlas-ammm.base:17707-17806)
+// abort_flag: optional device int; when non-zero at kernel start the update is skipped.
+template <typename T>
+void gemm(int TA, int TB, int M, int N, int K, T alpha, const T* A, size_t lda, const T* B, size_t ldb, T beta, T* C,
+          size_t ldc, const int* abort_flag = nullptr);
+
+// C(uplo) <- alpha*op(A)*op(A)^T + beta*C  (reference ATL_Xsyrk, Clint/l3micro.base:2688)
+template <typename T>
+void syrk(int uplo, int trans, int N, int K, T alpha, const T* A, size_t lda, T beta, T* C, size_t ldc,
+          const int* abort_flag = nullptr);
+
+// C(uplo) <- alpha*op(A)*op(A)^H + beta*C, alpha/beta real, Im(diag)=0 (reference ATL_Xherk, -DConj_)
+template <typename T>
+void herk(int uplo, int trans, int N, int K, typename ST<T>::real alpha, const T* A, size_t lda,
+          typename ST<T>::real beta, T* C, size_t ldc, const int* abort_flag = nullptr);
+
+// B <- alpha*op(A)*B or alpha*B*op(A), A triangular   (reference ATL_Xtrmm, Clint/trmm-micro.base:1942-2157)
+template <typename T>
+void trmm(int side, int uplo, int trans, int diag, int M, int N, T alpha, const T* A, size_t lda, T* B, size_t ldb);
+
+// solve op(A)*X = alpha*B or X*op(A) = alpha*B in place (reference ATL_Xtrsm, Clint/trsm-micro.base:350-424)
+template <typename T>
+void trsm(int side, int uplo, int trans, int diag, int M, int N, T alpha, const T* A, size_t lda, T* B, size_t ldb,
+          const int* abort_flag = nullptr);
+
+// Row interchanges (reference ATL_laswp, Clint/atlas-lp.base:1053); piv is a DEVICE array here.
+template <typename T>
+void laswp(int N, T* A, size_t lda, int K1, int K2, const int* d_piv, int inci);
+
+// Column-major recursive LU with partial pivoting (reference ATL_getrfC, Clint/atlas-lp.base:1497-1617).
+// d_ipiv: device int[min(M,N)], 0-based; d_info: device int, set to the 1-based index of the first
+// exactly-zero pivot (0 if none).  Everything stays on the stream.
+template <typename T>
+void getrf(int M, int N, T* A, size_t lda, int* d_ipiv, int* d_info);
+
+// Column-major recursive Cholesky (reference ATL_potrfL/U, Clint/atlas-lp.base:675-968).
+// d_info: device int (must be zero on entry), set to the 1-based index of the first non-positive
+// pivot; all work after the failing block is skipped on the device, like the reference's early return.
+template <typename T>
+void potrf(int uplo, int N, T* A, size_t lda, int* d_info);
+
+// Grow-only per-thread device workspace (freed by free_workspace()).
+void* workspace(size_t bytes, int slot = 0);
+void free_workspace();
+long long launch_count();
+void reset_launch_count();
+
+}  // namespace ab

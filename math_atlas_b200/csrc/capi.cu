@@ -1,0 +1,593 @@
+// C ABI of libatlas_b200.so: the link-time symbol set of the reference's libraries for the
+// level-3 / LU / Cholesky path (include/atlas_b200.h declares every entry point and cites the
+// reference interface it replaces).
+//
+//   cblas_X{gemm,syrk,herk,trsm,trmm}   reference Clint/cblas.base:98-693  (argument checks, cblas_errprn /
+//                                        cblas_xerbla texts and exit(-1), row-major folding, GEMM->SYRK shortcut)
+//   ATL_X{gemm,syrk,herk,trsm,trmm}     reference include/atlas_level3.h (Clint/atlas.base:20992)
+//   clapack_X{getrf,potrf}, ATL_X{getrf,potrf,laswp}   reference Clint/atlas-clp.base:140-362, atlas-lp.base:332,1053,1619
+//   X{gemm,syrk,herk,trsm,trmm,getrf,potrf}_           reference Antoine/atlF77blas.base + atlF77wrap.base,
+//                                        Clint/atlas-ilp.base:160 (1-based pivots), gfortran hidden string lengths
+//
+// New relative to the reference: every array argument may be a host OR a device pointer
+// (cudaPointerGetAttributes).  Host arrays are staged into device memory (cudaMemcpy2DAsync of
+// exactly rows x cols, so the lda gap is never read or written) and the outputs copied back;
+// device arrays are used in place.  Every call returns after the stream has drained (BLAS has no
+// asynchronous contract).  There is no CPU fallback: without a CUDA device the first call aborts.
+#include "ab_api.h"
+#include <cstdarg>
+#include <cstring>
+#include <cctype>
+#include <mutex>
+#include <memory>
+
+using namespace ab;
+
+// ------------------------------------------------------------------------------------- errors
+static int g_xerbla_exit = 1;
+static thread_local int g_last_xerbla_arg = 0;
+static thread_local char g_last_xerbla_rout[64] = {0};
+
+extern "C" {
+int cblas_errprn(int ierr, int info, const char* form, ...) {
+  va_list ap;
+  va_start(ap, form);
+  vfprintf(stderr, form, ap);
+  va_end(ap);
+  return ierr < info ? ierr : info;
+}
+void cblas_xerbla(int p, const char* rout, const char* form, ...) {
+  va_list ap;
+  va_start(ap, form);
+  if (p) fprintf(stderr, "Parameter %d to routine %s was incorrect\n", p, rout);
+  vfprintf(stderr, form, ap);
+  va_end(ap);
+  g_last_xerbla_arg = p;
+  strncpy(g_last_xerbla_rout, rout, sizeof(g_last_xerbla_rout) - 1);
+  if (g_xerbla_exit) exit(-1);
+}
+// F77 error handler (netlib XERBLA text; the reference's Fortran front ends call it, atlF77blas.base)
+__attribute__((weak)) void xerbla_(const char* srname, const int* info, size_t len) {
+  char nm[33];
+  size_t n = len < 32 ? len : 32;
+  memcpy(nm, srname, n);
+  nm[n] = 0;
+  fprintf(stderr, " ** On entry to %-6s parameter number %2d had an illegal value\n", nm, *info);
+  g_last_xerbla_arg = *info;
+  strncpy(g_last_xerbla_rout, nm, sizeof(g_last_xerbla_rout) - 1);
+  if (g_xerbla_exit) exit(-1);
+}
+// test hooks (not in the reference): keep the process alive on argument errors and read them back
+void atlb200_set_xerbla_exit(int on) { g_xerbla_exit = on; }
+int atlb200_last_xerbla(char* rout, int len) {
+  if (rout && len > 0) { strncpy(rout, g_last_xerbla_rout, (size_t)len - 1); rout[len - 1] = 0; }
+  int p = g_last_xerbla_arg;
+  g_last_xerbla_arg = 0;
+  g_last_xerbla_rout[0] = 0;
+  return p;
+}
+long long atlb200_launch_count(void) { return launch_count(); }
+void atlb200_reset_launch_count(void) { reset_launch_count(); }
+void atlb200_free_workspace(void) { free_workspace(); }
+void atlb200_set_stream(void* stream) { set_current_stream(static_cast<cudaStream_t>(stream)); }
+int atlb200_version(void) { return 100; }
+}
+
+// ------------------------------------------------------------------------------------- staging
+static bool is_device_ptr(const void* p) {
+  if (!p) return false;
+  cudaPointerAttributes at;
+  cudaError_t e = cudaPointerGetAttributes(&at, p);
+  if (e != cudaSuccess) { (void)cudaGetLastError(); return false; }
+  return at.type == cudaMemoryTypeDevice || at.type == cudaMemoryTypeManaged;
+}
+
+static void init_pool_once() {
+  static std::once_flag once;
+  std::call_once(once, [] {
+    int dev = 0, n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0) {
+      fprintf(stderr, "atlas_b200: no CUDA device available - this library has no CPU fallback\n");
+      abort();
+    }
+    AB_CUDA_CHECK(cudaGetDevice(&dev));
+    cudaMemPool_t pool;
+    AB_CUDA_CHECK(cudaDeviceGetDefaultMemPool(&pool, dev));
+    unsigned long long keep = ~0ull;   // keep staged buffers cached between calls
+    AB_CUDA_CHECK(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
+  });
+}
+
+// A rows x cols column-major operand that may live on the host: dev() is always a device pointer.
+template <typename T>
+struct Operand {
+  T* d = nullptr;          // device pointer to element (0,0)
+  size_t ld = 0;           // its leading dimension
+  T* h = nullptr;          // host origin when staged
+  size_t ldh = 0;
+  int rows = 0, cols = 0;
+  bool staged = false, out = false;
+  Operand(const T* p, int rows_, int cols_, size_t ld_, bool in, bool out_) : rows(rows_), cols(cols_), out(out_) {
+    if (rows <= 0 || cols <= 0 || !p) { d = const_cast<T*>(p); ld = ld_; return; }
+    if (is_device_ptr(p)) { d = const_cast<T*>(p); ld = ld_; return; }
+    init_pool_once();
+    staged = true; h = const_cast<T*>(p); ldh = ld_;
+    ld = ((size_t)rows + 15) & ~(size_t)15;   // 16-element pitch: every column 128-byte aligned (TMA friendly)
+    AB_CUDA_CHECK(cudaMallocAsync(&d, sizeof(T) * ld * (size_t)cols, current_stream()));
+    if (in)
+      AB_CUDA_CHECK(cudaMemcpy2DAsync(d, sizeof(T) * ld, h, sizeof(T) * ldh, sizeof(T) * (size_t)rows, (size_t)cols,
+                                      cudaMemcpyHostToDevice, current_stream()));
+  }
+  void finish() {
+    if (!staged) return;
+    if (out)
+      AB_CUDA_CHECK(cudaMemcpy2DAsync(h, sizeof(T) * ldh, d, sizeof(T) * ld, sizeof(T) * (size_t)rows, (size_t)cols,
+                                      cudaMemcpyDeviceToHost, current_stream()));
+    AB_CUDA_CHECK(cudaFreeAsync(d, current_stream()));
+    staged = false;
+  }
+};
+
+static void sync_stream() { AB_CUDA_CHECK(cudaStreamSynchronize(current_stream())); }
+
+// small device scratch for info / pivots when the caller's are on the host
+struct DevInts {
+  int* d = nullptr; int* h = nullptr; int n = 0; bool staged = false;
+  DevInts(int* p, int n_, bool in) : n(n_) {
+    if (n <= 0) { d = p; return; }
+    if (p && is_device_ptr(p)) { d = p; return; }
+    init_pool_once();
+    staged = true; h = p;
+    AB_CUDA_CHECK(cudaMallocAsync(&d, sizeof(int) * (size_t)n, current_stream()));
+    if (in && h) AB_CUDA_CHECK(cudaMemcpyAsync(d, h, sizeof(int) * (size_t)n, cudaMemcpyHostToDevice, current_stream()));
+  }
+  void finish(bool out) {
+    if (!staged) return;
+    if (out && h) AB_CUDA_CHECK(cudaMemcpyAsync(h, d, sizeof(int) * (size_t)n, cudaMemcpyDeviceToHost, current_stream()));
+    AB_CUDA_CHECK(cudaFreeAsync(d, current_stream()));
+    staged = false;
+  }
+};
+
+// ------------------------------------------------------------------------------------- ATL_* level (column-major, unchecked)
+template <typename T>
+static void atl_gemm(int TA, int TB, size_t M, size_t N, size_t K, T alpha, const T* A, size_t lda, const T* B, size_t ldb,
+                     T beta, T* C, size_t ldc) {
+  if (M == 0 || N == 0) return;
+  const bool needAB = !(ST<T>::is_zero(alpha) || K == 0);
+  const bool tA = (TA == TransT || TA == ConjTrans), tB = (TB == TransT || TB == ConjTrans);
+  Operand<T> a(A, needAB ? (int)(tA ? K : M) : 0, needAB ? (int)(tA ? M : K) : 0, lda, true, false);
+  Operand<T> b(B, needAB ? (int)(tB ? N : K) : 0, needAB ? (int)(tB ? K : N) : 0, ldb, true, false);
+  Operand<T> c(C, (int)M, (int)N, ldc, !ST<T>::is_zero(beta), true);
+  gemm<T>(TA, TB, (int)M, (int)N, (int)K, alpha, a.d, a.ld, b.d, b.ld, beta, c.d, c.ld);
+  a.finish(); b.finish(); c.finish();
+  sync_stream();
+}
+
+template <typename T>
+static void atl_syrk(int uplo, int trans, size_t N, size_t K, T alpha, const T* A, size_t lda, T beta, T* C, size_t ldc) {
+  if (N == 0) return;
+  const bool needA = !(ST<T>::is_zero(alpha) || K == 0);
+  const bool tA = (trans != NoTrans);
+  Operand<T> a(A, needA ? (int)(tA ? K : N) : 0, needA ? (int)(tA ? N : K) : 0, lda, true, false);
+  Operand<T> c(C, (int)N, (int)N, ldc, true, true);   // the untouched triangle must survive the round trip
+  syrk<T>(uplo, trans, (int)N, (int)K, alpha, a.d, a.ld, beta, c.d, c.ld);
+  a.finish(); c.finish();
+  sync_stream();
+}
+
+template <typename T>
+static void atl_herk(int uplo, int trans, size_t N, size_t K, typename ST<T>::real alpha, const T* A, size_t lda,
+                     typename ST<T>::real beta, T* C, size_t ldc) {
+  if (N == 0) return;
+  const bool needA = !(alpha == 0 || K == 0);
+  const bool tA = (trans != NoTrans);
+  Operand<T> a(A, needA ? (int)(tA ? K : N) : 0, needA ? (int)(tA ? N : K) : 0, lda, true, false);
+  Operand<T> c(C, (int)N, (int)N, ldc, true, true);
+  herk<T>(uplo, trans, (int)N, (int)K, alpha, a.d, a.ld, beta, c.d, c.ld);
+  a.finish(); c.finish();
+  sync_stream();
+}
+
+template <typename T>
+static void atl_trxm(bool solve, int side, int uplo, int trans, int diag, size_t M, size_t N, T alpha, const T* A, size_t lda,
+                     T* B, size_t ldb) {
+  if (M == 0 || N == 0) return;
+  const int nA = (int)(side == Left ? M : N);
+  const bool needA = !ST<T>::is_zero(alpha);
+  Operand<T> a(A, needA ? nA : 0, needA ? nA : 0, lda, true, false);
+  Operand<T> b(B, (int)M, (int)N, ldb, needA, true);
+  if (solve) trsm<T>(side, uplo, trans, diag, (int)M, (int)N, alpha, a.d, a.ld, b.d, b.ld);
+  else trmm<T>(side, uplo, trans, diag, (int)M, (int)N, alpha, a.d, a.ld, b.d, b.ld);
+  a.finish(); b.finish();
+  sync_stream();
+}
+
+template <typename T>
+__global__ void syreflect_kernel(int N, T* C, size_t ldc) {   // copy the Upper triangle into the Lower (ATL_Xsyreflect)
+  const int i = blockIdx.x * blockDim.x + threadIdx.x, j = blockIdx.y * blockDim.y + threadIdx.y;
+  if (i < N && j < N && i > j) C[(size_t)i + (size_t)j * ldc] = C[(size_t)j + (size_t)i * ldc];
+}
+
+template <typename T>
+static int atl_getrf(int order, int M, int N, T* A, int lda, int* ipiv) {
+  // RowMajor M x N is the column-major N x M matrix in the same memory: A = L U P there is
+  // P' A^T = L' U' here (reference ATL_getrfR, atlas-lp.base:1210-1297).
+  const int rows = (order == ColMajor) ? M : N, cols = (order == ColMajor) ? N : M;
+  const int MN = M < N ? M : N;
+  if (MN <= 0) return 0;
+  Operand<T> a(A, rows, cols, (size_t)lda, true, true);
+  DevInts piv(ipiv, MN, false);
+  int h_info = 0;
+  DevInts info(&h_info, 1, false);
+  getrf<T>(rows, cols, a.d, a.ld, piv.d, info.d);
+  a.finish(); piv.finish(true); info.finish(true);
+  sync_stream();
+  return h_info;
+}
+
+template <typename T>
+static int atl_potrf(int order, int uplo, int N, T* A, int lda) {
+  if (N <= 0) return 0;
+  // RowMajor: the same memory viewed column-major holds the other triangle (conjugated for
+  // complex, still Hermitian positive definite), reference atlas-lp.base:336-373
+  const int ul = (order == ColMajor) ? uplo : (uplo == Upper ? Lower : Upper);
+  Operand<T> a(A, N, N, (size_t)lda, true, true);
+  int h_info = 0;
+  DevInts info(&h_info, 1, false);
+  potrf<T>(ul, N, a.d, a.ld, info.d);
+  a.finish(); info.finish(true);
+  sync_stream();
+  return h_info;
+}
+
+template <typename T>
+static void atl_laswp(int N, T* A, int lda, int K1, int K2, const int* piv, int inci) {
+  if (N <= 0 || K2 <= K1) return;
+  // The entry for row i is piv[i*|inci|] in both directions (the sign of inci only reverses the
+  // order of application, atlas-lp.base:1053-1166).  A host matrix is staged up to the largest
+  // row index referenced, since the interface does not carry the row count.
+  const int ainc = inci < 0 ? -inci : inci;
+  const int npiv = (K2 - 1) * ainc + 1;
+  std::unique_ptr<int[]> tmp;
+  const int* hp = piv;
+  if (is_device_ptr(piv)) {
+    tmp.reset(new int[npiv]);
+    AB_CUDA_CHECK(cudaMemcpy(tmp.get(), piv, sizeof(int) * (size_t)npiv, cudaMemcpyDeviceToHost));
+    hp = tmp.get();
+  }
+  int maxrow = K2 - 1;
+  for (int i = K1; i < K2; i++) { const int ip = hp[(size_t)i * ainc]; if (ip > maxrow) maxrow = ip; }
+  Operand<T> a(A, maxrow + 1, N, (size_t)lda, true, true);
+  DevInts dp(const_cast<int*>(piv), npiv, true);
+  laswp<T>(N, a.d, a.ld, K1, K2, dp.d, inci);
+  a.finish(); dp.finish(false);
+  sync_stream();
+}
+
+// ------------------------------------------------------------------------------------- CBLAS level (checked)
+#define BAD_TRANS(t) ((t) != ConjTrans && (t) != TransT)
+
+template <typename T>
+static void cb_gemm(const char* rout, int Order, int TA, int TB, int M, int N, int K, T alpha, const T* A, int lda, const T* B,
+                    int ldb, T beta, T* C, int ldc) {
+  int info = 2000;
+  if (M < 0) info = cblas_errprn(4, info, "M cannot be less than zero 0,; is set to %d.", M);
+  if (N < 0) info = cblas_errprn(5, info, "N cannot be less than zero 0,; is set to %d.", N);
+  if (K < 0) info = cblas_errprn(6, info, "K cannot be less than zero 0,; is set to %d.", K);
+  if (Order == RowMajor || Order == ColMajor) {
+    const bool col = (Order == ColMajor);
+    const int a_nt = col ? M : K, a_t = col ? K : M;    // required lda for NoTrans / Trans
+    const int b_nt = col ? K : N, b_t = col ? N : K;
+    const int c_req = col ? M : N;
+    if (TA == NoTrans) { if (lda < a_nt || lda < 1) info = cblas_errprn(9, info, "lda must be >= MAX(%c,1): lda=%d %c=%d", col ? 'M' : 'K', lda, col ? 'M' : 'K', a_nt); }
+    else {
+      if (BAD_TRANS(TA)) info = cblas_errprn(2, info, "TransA must be %d, %d or %d, but is set to %d", NoTrans, TransT, ConjTrans, TA);
+      if (lda < a_t || lda < 1) info = cblas_errprn(9, info, "lda must be >= MAX(%c,1): lda=%d %c=%d", col ? 'K' : 'M', lda, col ? 'K' : 'M', a_t);
+    }
+    if (TB == NoTrans) { if (ldb < b_nt || ldb < 1) info = cblas_errprn(11, info, "ldb must be >= MAX(%c,1): ldb=%d %c=%d", col ? 'K' : 'N', ldb, col ? 'K' : 'N', b_nt); }
+    else {
+      if (BAD_TRANS(TB)) info = cblas_errprn(3, info, "TransB must be %d, %d or %d, but is set to %d", NoTrans, TransT, ConjTrans, TB);
+      if (ldb < b_t || ldb < 1) info = cblas_errprn(11, info, "ldb must be >= MAX(%c,1): ldb=%d %c=%d", col ? 'N' : 'K', ldb, col ? 'N' : 'K', b_t);
+    }
+    if (ldc < c_req || ldc < 1) info = cblas_errprn(14, info, "ldc must be >= MAX(%c,1): ldc=%d %c=%d", col ? 'M' : 'N', ldc, col ? 'M' : 'N', c_req);
+  } else info = cblas_errprn(1, info, "Order must be %d or %d, but is set to %d", RowMajor, ColMajor, Order);
+  if (info != 2000) { cblas_xerbla(info, rout, ""); return; }
+  // GEMM -> SYRK shortcut (cblas.base:221-229): C = A*A^T computed on one triangle, then reflected
+  if (A == B && M == N && TA != TB && lda == ldb && ST<T>::is_zero(beta) && TA != ConjTrans && TB != ConjTrans) {
+    if (N == 0) return;
+    const int tr = (Order == ColMajor) ? TA : TB;
+    const bool needA = !(ST<T>::is_zero(alpha) || K == 0);
+    const bool tA = (tr != NoTrans);
+    Operand<T> a(A, needA ? (tA ? K : N) : 0, needA ? (tA ? N : K) : 0, (size_t)lda, true, false);
+    Operand<T> c(C, N, N, (size_t)ldc, false, true);
+    syrk<T>(Upper, tr, N, K, alpha, a.d, a.ld, beta, c.d, c.ld);
+    dim3 blk(32, 8), grd((N + 31) / 32, (N + 7) / 8);
+    syreflect_kernel<T><<<grd, blk, 0, current_stream()>>>(N, c.d, c.ld);
+    count_launch();
+    a.finish(); c.finish();
+    sync_stream();
+    return;
+  }
+  if (Order == ColMajor) atl_gemm<T>(TA, TB, M, N, K, alpha, A, lda, B, ldb, beta, C, ldc);
+  else atl_gemm<T>(TB, TA, N, M, K, alpha, B, ldb, A, lda, beta, C, ldc);
+}
+
+template <typename T>
+static bool check_syrk(const char* rout, bool herk, int Order, int Uplo, int Trans, int N, int K, int lda, int ldc) {
+  int info = 2000;
+  if (Uplo != Upper && Uplo != Lower) info = cblas_errprn(2, info, "UPLO must be %d or %d, but is set to %d", Upper, Lower, Uplo);
+  if (N < 0) info = cblas_errprn(4, info, "N cannot be less than zero; it is set to %d.", N);
+  if (K < 0) info = cblas_errprn(5, info, "K cannot be less than zero; it is set to %d.", K);
+  if (Order == ColMajor || Order == RowMajor) {
+    const bool col = (Order == ColMajor);
+    if (Trans == NoTrans) {
+      const int req = col ? N : K;
+      if (lda < req || lda < 1) info = cblas_errprn(8, info, "lda must be >= MAX(%c,1): lda=%d %c=%d", col ? 'N' : 'K', lda, col ? 'N' : 'K', req);
+    } else {
+      const bool ok = herk ? (Trans == ConjTrans) : (Trans == TransT || Trans == ConjTrans);
+      if (!ok) info = cblas_errprn(3, info, "Trans must be %d or %d, but is set to %d", NoTrans, herk ? ConjTrans : TransT, Trans);
+      const int req = col ? K : N;
+      if (lda < req || lda < 1) info = cblas_errprn(8, info, "lda must be >= MAX(%c,1): lda=%d %c=%d", col ? 'K' : 'N', lda, col ? 'K' : 'N', req);
+    }
+  } else info = cblas_errprn(1, info, "Order must be %d or %d, but is set to %d", RowMajor, ColMajor, Order);
+  if (ldc < N || ldc < 1) info = cblas_errprn(11, info, "ldc must be >= MAX(N,1): ldc=%d N=%d", ldc, N);
+  if (info != 2000) { cblas_xerbla(info, rout, ""); return false; }
+  return true;
+}
+
+template <typename T>
+static void cb_syrk(const char* rout, int Order, int Uplo, int Trans, int N, int K, T alpha, const T* A, int lda, T beta, T* C, int ldc) {
+  if (!check_syrk<T>(rout, false, Order, Uplo, Trans, N, K, lda, ldc)) return;
+  if (Order == ColMajor) atl_syrk<T>(Uplo, Trans, N, K, alpha, A, lda, beta, C, ldc);
+  else atl_syrk<T>(Uplo == Upper ? Lower : Upper, Trans == NoTrans ? TransT : NoTrans, N, K, alpha, A, lda, beta, C, ldc);
+}
+template <typename T>
+static void cb_herk(const char* rout, int Order, int Uplo, int Trans, int N, int K, typename ST<T>::real alpha, const T* A, int lda,
+                    typename ST<T>::real beta, T* C, int ldc) {
+  if (!check_syrk<T>(rout, true, Order, Uplo, Trans, N, K, lda, ldc)) return;
+  if (Order == ColMajor) atl_herk<T>(Uplo, Trans, N, K, alpha, A, lda, beta, C, ldc);
+  else atl_herk<T>(Uplo == Upper ? Lower : Upper, Trans == NoTrans ? ConjTrans : NoTrans, N, K, alpha, A, lda, beta, C, ldc);
+}
+
+template <typename T>
+static void cb_trxm(const char* rout, bool solve, int Order, int Side, int Uplo, int TA, int Diag, int M, int N, T alpha, const T* A,
+                    int lda, T* B, int ldb) {
+  int info = 2000;
+  if (Order == ColMajor || Order == RowMajor) {
+    if (Side == Left) { if (lda < M || lda < 1) info = cblas_errprn(10, info, "lda must be >= MAX(M,1): lda=%d M=%d", lda, M); }
+    else if (Side == Right) { if (lda < N || lda < 1) info = cblas_errprn(10, info, "lda must be >= MAX(N,1): lda=%d N=%d", lda, N); }
+    else info = cblas_errprn(2, info, "SIDE must be %d or %d, but is set to %d", Right, Left, Side);
+    const int req = (Order == ColMajor) ? M : N;
+    if (ldb < req || ldb < 1) info = cblas_errprn(12, info, "ldb must be >= MAX(%c,1): ldb=%d %c=%d", Order == ColMajor ? 'M' : 'N', ldb, Order == ColMajor ? 'M' : 'N', req);
+  } else info = cblas_errprn(1, info, "Order must be %d or %d, but is set to %d", RowMajor, ColMajor, Order);
+  if (Uplo != Upper && Uplo != Lower) info = cblas_errprn(3, info, "UPLO must be %d or %d, but is set to %d", Upper, Lower, Uplo);
+  if (TA != NoTrans && TA != TransT && TA != ConjTrans) info = cblas_errprn(4, info, "TransA must be %d, %d or %d, but is set to %d", NoTrans, TransT, ConjTrans, TA);
+  if (Diag != Unit && Diag != NonUnit) info = cblas_errprn(5, info, "UPLO must be %d or %d, but is set to %d", Unit, NonUnit, Diag);
+  if (M < 0) info = cblas_errprn(6, info, "M cannot be less than zero; it is set to %d.", M);
+  if (N < 0) info = cblas_errprn(7, info, "N cannot be less than zero; it is set to %d.", N);
+  if (info != 2000) { cblas_xerbla(info, rout, ""); return; }
+  if (Order == ColMajor) atl_trxm<T>(solve, Side, Uplo, TA, Diag, M, N, alpha, A, lda, B, ldb);
+  else atl_trxm<T>(solve, Side == Left ? Right : Left, Uplo == Upper ? Lower : Upper, TA, Diag, N, M, alpha, A, lda, B, ldb);
+}
+
+template <typename T>
+static int cl_getrf(const char* rout, int Order, int M, int N, T* A, int lda, int* ipiv) {
+  int ierr = 0;
+  if (Order != RowMajor && Order != ColMajor) { ierr = -1; cblas_xerbla(1, rout, "Order must be %d or %d, but is set to %d\n", RowMajor, ColMajor, Order); }
+  if (M < 0) { ierr = -2; cblas_xerbla(2, rout, "M cannot be less than zero 0,; is set to %d.\n", M); }
+  if (N < 0) { ierr = -3; cblas_xerbla(3, rout, "N cannot be less than zero 0,; is set to %d.\n", N); }
+  if (Order == ColMajor) { if (lda < M || lda < 1) { ierr = -6; cblas_xerbla(6, rout, "lda must be >= MAX(M,1): lda=%d M=%d\n", lda, M); } }
+  else if (lda < N || lda < 1) { ierr = -6; cblas_xerbla(6, rout, "lda must be >= MAX(N,1): lda=%d N=%d\n", lda, N); }
+  if (!ierr) ierr = atl_getrf<T>(Order, M, N, A, lda, ipiv);
+  return ierr;
+}
+template <typename T>
+static int cl_potrf(const char* rout, int Order, int Uplo, int N, T* A, int lda) {
+  int ierr = 0;
+  if (Order != RowMajor && Order != ColMajor) { ierr = -1; cblas_xerbla(1, rout, "Order must be %d or %d, but is set to %d\n", RowMajor, ColMajor, Order); }
+  if (Uplo != Upper && Uplo != Lower) { ierr = -2; cblas_xerbla(2, rout, "Uplo must be %d or %d, but is set to %d\n", Upper, Lower, Uplo); }
+  if (N < 0) { ierr = -3; cblas_xerbla(3, rout, "N cannot be less than zero 0,; is set to %d.\n", N); }
+  if (lda < N || lda < 1) { ierr = -5; cblas_xerbla(5, rout, "lda must be >= MAX(N,1): lda=%d N=%d\n", lda, N); }
+  if (!ierr) ierr = atl_potrf<T>(Order, Uplo, N, A, lda);
+  return ierr;
+}
+
+// ------------------------------------------------------------------------------------- F77 helpers
+static int f_trans(const char* c) { switch (toupper((unsigned char)*c)) { case 'N': return NoTrans; case 'T': return TransT; case 'C': return ConjTrans; } return -1; }
+static int f_uplo(const char* c) { switch (toupper((unsigned char)*c)) { case 'U': return Upper; case 'L': return Lower; } return -1; }
+static int f_side(const char* c) { switch (toupper((unsigned char)*c)) { case 'L': return Left; case 'R': return Right; } return -1; }
+static int f_diag(const char* c) { switch (toupper((unsigned char)*c)) { case 'N': return NonUnit; case 'U': return Unit; } return -1; }
+static bool f_err(const char* name, int info) { if (!info) return false; xerbla_(name, &info, strlen(name)); return true; }
+static inline int imax(int a, int b) { return a > b ? a : b; }
+
+template <typename T>
+static void f_gemm(const char* name, const char* ta, const char* tb, const int* m, const int* n, const int* k, const T* alpha,
+                   const T* A, const int* lda, const T* B, const int* ldb, const T* beta, T* C, const int* ldc) {
+  const int TA = f_trans(ta), TB = f_trans(tb);
+  const int nrowa = (TA == NoTrans) ? *m : *k, nrowb = (TB == NoTrans) ? *k : *n;
+  int info = 0;   // netlib xGEMM argument numbering
+  if (TA < 0) info = 1;
+  else if (TB < 0) info = 2;
+  else if (*m < 0) info = 3;
+  else if (*n < 0) info = 4;
+  else if (*k < 0) info = 5;
+  else if (*lda < imax(1, nrowa)) info = 8;
+  else if (*ldb < imax(1, nrowb)) info = 10;
+  else if (*ldc < imax(1, *m)) info = 13;
+  if (f_err(name, info)) return;
+  atl_gemm<T>(TA, TB, *m, *n, *k, *alpha, A, *lda, B, *ldb, *beta, C, *ldc);
+}
+template <typename T>
+static void f_syrk(const char* name, const char* ul, const char* tr, const int* n, const int* k, const T* alpha, const T* A,
+                   const int* lda, const T* beta, T* C, const int* ldc) {
+  const int UL = f_uplo(ul), TR = f_trans(tr);
+  const int nrowa = (TR == NoTrans) ? *n : *k;
+  int info = 0;
+  if (UL < 0) info = 1;
+  else if (TR < 0 || (ST<T>::cplx && TR == ConjTrans)) info = 2;
+  else if (*n < 0) info = 3;
+  else if (*k < 0) info = 4;
+  else if (*lda < imax(1, nrowa)) info = 7;
+  else if (*ldc < imax(1, *n)) info = 10;
+  if (f_err(name, info)) return;
+  atl_syrk<T>(UL, TR == NoTrans ? NoTrans : TransT, *n, *k, *alpha, A, *lda, *beta, C, *ldc);
+}
+template <typename T>
+static void f_herk(const char* name, const char* ul, const char* tr, const int* n, const int* k, const typename ST<T>::real* alpha,
+                   const T* A, const int* lda, const typename ST<T>::real* beta, T* C, const int* ldc) {
+  const int UL = f_uplo(ul), TR = f_trans(tr);
+  const int nrowa = (TR == NoTrans) ? *n : *k;
+  int info = 0;
+  if (UL < 0) info = 1;
+  else if (TR != NoTrans && TR != ConjTrans) info = 2;
+  else if (*n < 0) info = 3;
+  else if (*k < 0) info = 4;
+  else if (*lda < imax(1, nrowa)) info = 7;
+  else if (*ldc < imax(1, *n)) info = 10;
+  if (f_err(name, info)) return;
+  atl_herk<T>(UL, TR, *n, *k, *alpha, A, *lda, *beta, C, *ldc);
+}
+template <typename T>
+static void f_trxm(const char* name, bool solve, const char* sd, const char* ul, const char* ta, const char* dg, const int* m,
+                   const int* n, const T* alpha, const T* A, const int* lda, T* B, const int* ldb) {
+  const int SD = f_side(sd), UL = f_uplo(ul), TA = f_trans(ta), DG = f_diag(dg);
+  const int nrowa = (SD == Left) ? *m : *n;
+  int info = 0;
+  if (SD < 0) info = 1;
+  else if (UL < 0) info = 2;
+  else if (TA < 0) info = 3;
+  else if (DG < 0) info = 4;
+  else if (*m < 0) info = 5;
+  else if (*n < 0) info = 6;
+  else if (*lda < imax(1, nrowa)) info = 9;
+  else if (*ldb < imax(1, *m)) info = 11;
+  if (f_err(name, info)) return;
+  atl_trxm<T>(solve, SD, UL, TA, DG, *m, *n, *alpha, A, *lda, B, *ldb);
+}
+template <typename T>
+static void f_getrf(const char* name, const int* m, const int* n, T* A, const int* lda, int* ipiv, int* info) {
+  *info = 0;
+  if (*m < 0) *info = -1;
+  else if (*n < 0) *info = -2;
+  else if (*lda < imax(1, *m)) *info = -4;
+  if (*info) { int p = -*info; xerbla_(name, &p, strlen(name)); return; }
+  const int MN = *m < *n ? *m : *n;
+  if (MN == 0) return;
+  // pivots come back 0-based; Fortran callers get them 1-based (atlas-ilp.base:160)
+  if (is_device_ptr(ipiv)) { fprintf(stderr, "atlas_b200: %s needs a host ipiv array\n", name); abort(); }
+  *info = atl_getrf<T>(ColMajor, *m, *n, A, *lda, ipiv);
+  for (int i = 0; i < MN; i++) ipiv[i]++;
+}
+template <typename T>
+static void f_potrf(const char* name, const char* ul, const int* n, T* A, const int* lda, int* info) {
+  const int UL = f_uplo(ul);
+  *info = 0;
+  if (UL < 0) *info = -1;
+  else if (*n < 0) *info = -2;
+  else if (*lda < imax(1, *n)) *info = -4;
+  if (*info) { int p = -*info; xerbla_(name, &p, strlen(name)); return; }
+  *info = atl_potrf<T>(ColMajor, UL, *n, A, *lda);
+}
+
+// ------------------------------------------------------------------------------------- exported symbols
+typedef float2 cfloat;
+typedef double2 cdouble;
+#define CS(T, p) (*reinterpret_cast<const T*>(p))
+#define CP(T, p) (reinterpret_cast<const T*>(p))
+#define MP(T, p) (reinterpret_cast<T*>(p))
+
+extern "C" {
+// ---- real types: scalars by value
+#define REAL_API(P, T, UP)                                                                                                      \
+  void cblas_##P##gemm(int Order, int TA, int TB, int M, int N, int K, T alpha, const T* A, int lda, const T* B, int ldb,      \
+                       T beta, T* C, int ldc) { cb_gemm<T>("cblas_" #P "gemm", Order, TA, TB, M, N, K, alpha, A, lda, B, ldb, beta, C, ldc); } \
+  void cblas_##P##syrk(int Order, int Uplo, int Trans, int N, int K, T alpha, const T* A, int lda, T beta, T* C, int ldc) {     \
+    cb_syrk<T>("cblas_" #P "syrk", Order, Uplo, Trans, N, K, alpha, A, lda, beta, C, ldc); }                                    \
+  void cblas_##P##trsm(int Order, int Side, int Uplo, int TA, int Diag, int M, int N, T alpha, const T* A, int lda, T* B,       \
+                       int ldb) { cb_trxm<T>("cblas_" #P "trsm", true, Order, Side, Uplo, TA, Diag, M, N, alpha, A, lda, B, ldb); } \
+  void cblas_##P##trmm(int Order, int Side, int Uplo, int TA, int Diag, int M, int N, T alpha, const T* A, int lda, T* B,       \
+                       int ldb) { cb_trxm<T>("cblas_" #P "trmm", false, Order, Side, Uplo, TA, Diag, M, N, alpha, A, lda, B, ldb); } \
+  void ATL_##P##gemm(int TA, int TB, size_t M, size_t N, size_t K, T alpha, const T* A, size_t lda, const T* B, size_t ldb,     \
+                     T beta, T* C, size_t ldc) { atl_gemm<T>(TA, TB, M, N, K, alpha, A, lda, B, ldb, beta, C, ldc); }           \
+  void ATL_##P##syrk(int Uplo, int Trans, size_t N, size_t K, T alpha, const T* A, size_t lda, T beta, T* C, size_t ldc) {      \
+    atl_syrk<T>(Uplo, Trans, N, K, alpha, A, lda, beta, C, ldc); }                                                              \
+  void ATL_##P##trsm(int Side, int Uplo, int TA, int Diag, size_t M, size_t N, T alpha, const T* A, size_t lda, T* B,           \
+                     size_t ldb) { atl_trxm<T>(true, Side, Uplo, TA, Diag, M, N, alpha, A, lda, B, ldb); }                      \
+  void ATL_##P##trmm(int Side, int Uplo, int TA, int Diag, size_t M, size_t N, T alpha, const T* A, size_t lda, T* B,           \
+                     size_t ldb) { atl_trxm<T>(false, Side, Uplo, TA, Diag, M, N, alpha, A, lda, B, ldb); }                     \
+  int clapack_##P##getrf(int Order, int M, int N, T* A, int lda, int* ipiv) { return cl_getrf<T>("clapack_" #P "getrf", Order, M, N, A, lda, ipiv); } \
+  int clapack_##P##potrf(int Order, int Uplo, int N, T* A, int lda) { return cl_potrf<T>("clapack_" #P "potrf", Order, Uplo, N, A, lda); } \
+  int ATL_##P##getrf(int Order, int M, int N, T* A, int lda, int* ipiv) { return atl_getrf<T>(Order, M, N, A, lda, ipiv); }     \
+  int ATL_##P##potrf(int Order, int Uplo, int N, T* A, int lda) { return atl_potrf<T>(Order, Uplo, N, A, lda); }                \
+  void ATL_##P##laswp(int N, T* A, int lda, int K1, int K2, const int* piv, int inci) { atl_laswp<T>(N, A, lda, K1, K2, piv, inci); } \
+  void P##gemm_(const char* ta, const char* tb, const int* m, const int* n, const int* k, const T* alpha, const T* A,           \
+                const int* lda, const T* B, const int* ldb, const T* beta, T* C, const int* ldc, size_t, size_t) {              \
+    f_gemm<T>(UP "GEMM ", ta, tb, m, n, k, alpha, A, lda, B, ldb, beta, C, ldc); }                                              \
+  void P##syrk_(const char* ul, const char* tr, const int* n, const int* k, const T* alpha, const T* A, const int* lda,         \
+                const T* beta, T* C, const int* ldc, size_t, size_t) { f_syrk<T>(UP "SYRK ", ul, tr, n, k, alpha, A, lda, beta, C, ldc); } \
+  void P##trsm_(const char* sd, const char* ul, const char* ta, const char* dg, const int* m, const int* n, const T* alpha,     \
+                const T* A, const int* lda, T* B, const int* ldb, size_t, size_t, size_t, size_t) {                             \
+    f_trxm<T>(UP "TRSM ", true, sd, ul, ta, dg, m, n, alpha, A, lda, B, ldb); }                                                 \
+  void P##trmm_(const char* sd, const char* ul, const char* ta, const char* dg, const int* m, const int* n, const T* alpha,     \
+                const T* A, const int* lda, T* B, const int* ldb, size_t, size_t, size_t, size_t) {                             \
+    f_trxm<T>(UP "TRMM ", false, sd, ul, ta, dg, m, n, alpha, A, lda, B, ldb); }                                                \
+  void P##getrf_(const int* m, const int* n, T* A, const int* lda, int* ipiv, int* info) { f_getrf<T>(UP "GETRF", m, n, A, lda, ipiv, info); } \
+  void P##potrf_(const char* ul, const int* n, T* A, const int* lda, int* info, size_t) { f_potrf<T>(UP "POTRF", ul, n, A, lda, info); }
+
+REAL_API(s, float, "S")
+REAL_API(d, double, "D")
+
+// ---- complex types: scalars by pointer, arrays as void* (interleaved re,im)
+#define CPLX_API(P, T, R, UP)                                                                                                   \
+  void cblas_##P##gemm(int Order, int TA, int TB, int M, int N, int K, const void* alpha, const void* A, int lda,               \
+                       const void* B, int ldb, const void* beta, void* C, int ldc) {                                           \
+    cb_gemm<T>("cblas_" #P "gemm", Order, TA, TB, M, N, K, CS(T, alpha), CP(T, A), lda, CP(T, B), ldb, CS(T, beta), MP(T, C), ldc); } \
+  void cblas_##P##syrk(int Order, int Uplo, int Trans, int N, int K, const void* alpha, const void* A, int lda,                 \
+                       const void* beta, void* C, int ldc) {                                                                   \
+    cb_syrk<T>("cblas_" #P "syrk", Order, Uplo, Trans, N, K, CS(T, alpha), CP(T, A), lda, CS(T, beta), MP(T, C), ldc); }         \
+  void cblas_##P##herk(int Order, int Uplo, int Trans, int N, int K, R alpha, const void* A, int lda, R beta, void* C,          \
+                       int ldc) { cb_herk<T>("cblas_" #P "herk", Order, Uplo, Trans, N, K, alpha, CP(T, A), lda, beta, MP(T, C), ldc); } \
+  void cblas_##P##trsm(int Order, int Side, int Uplo, int TA, int Diag, int M, int N, const void* alpha, const void* A,         \
+                       int lda, void* B, int ldb) {                                                                            \
+    cb_trxm<T>("cblas_" #P "trsm", true, Order, Side, Uplo, TA, Diag, M, N, CS(T, alpha), CP(T, A), lda, MP(T, B), ldb); }       \
+  void cblas_##P##trmm(int Order, int Side, int Uplo, int TA, int Diag, int M, int N, const void* alpha, const void* A,         \
+                       int lda, void* B, int ldb) {                                                                            \
+    cb_trxm<T>("cblas_" #P "trmm", false, Order, Side, Uplo, TA, Diag, M, N, CS(T, alpha), CP(T, A), lda, MP(T, B), ldb); }      \
+  void ATL_##P##gemm(int TA, int TB, size_t M, size_t N, size_t K, const R* alpha, const R* A, size_t lda, const R* B,          \
+                     size_t ldb, const R* beta, R* C, size_t ldc) {                                                            \
+    atl_gemm<T>(TA, TB, M, N, K, CS(T, alpha), CP(T, A), lda, CP(T, B), ldb, CS(T, beta), MP(T, C), ldc); }                     \
+  void ATL_##P##syrk(int Uplo, int Trans, size_t N, size_t K, const R* alpha, const R* A, size_t lda, const R* beta, R* C,      \
+                     size_t ldc) { atl_syrk<T>(Uplo, Trans, N, K, CS(T, alpha), CP(T, A), lda, CS(T, beta), MP(T, C), ldc); }   \
+  void ATL_##P##herk(int Uplo, int Trans, size_t N, size_t K, R alpha, const R* A, size_t lda, R beta, R* C, size_t ldc) {      \
+    atl_herk<T>(Uplo, Trans, N, K, alpha, CP(T, A), lda, beta, MP(T, C), ldc); }                                                \
+  void ATL_##P##trsm(int Side, int Uplo, int TA, int Diag, size_t M, size_t N, const R* alpha, const R* A, size_t lda, R* B,    \
+                     size_t ldb) { atl_trxm<T>(true, Side, Uplo, TA, Diag, M, N, CS(T, alpha), CP(T, A), lda, MP(T, B), ldb); } \
+  void ATL_##P##trmm(int Side, int Uplo, int TA, int Diag, size_t M, size_t N, const R* alpha, const R* A, size_t lda, R* B,    \
+                     size_t ldb) { atl_trxm<T>(false, Side, Uplo, TA, Diag, M, N, CS(T, alpha), CP(T, A), lda, MP(T, B), ldb); } \
+  int clapack_##P##getrf(int Order, int M, int N, void* A, int lda, int* ipiv) { return cl_getrf<T>("clapack_" #P "getrf", Order, M, N, MP(T, A), lda, ipiv); } \
+  int clapack_##P##potrf(int Order, int Uplo, int N, void* A, int lda) { return cl_potrf<T>("clapack_" #P "potrf", Order, Uplo, N, MP(T, A), lda); } \
+  int ATL_##P##getrf(int Order, int M, int N, R* A, int lda, int* ipiv) { return atl_getrf<T>(Order, M, N, MP(T, A), lda, ipiv); } \
+  int ATL_##P##potrf(int Order, int Uplo, int N, R* A, int lda) { return atl_potrf<T>(Order, Uplo, N, MP(T, A), lda); }         \
+  void ATL_##P##laswp(int N, R* A, int lda, int K1, int K2, const int* piv, int inci) { atl_laswp<T>(N, MP(T, A), lda, K1, K2, piv, inci); } \
+  void P##gemm_(const char* ta, const char* tb, const int* m, const int* n, const int* k, const void* alpha, const void* A,     \
+                const int* lda, const void* B, const int* ldb, const void* beta, void* C, const int* ldc, size_t, size_t) {     \
+    f_gemm<T>(UP "GEMM ", ta, tb, m, n, k, CP(T, alpha), CP(T, A), lda, CP(T, B), ldb, CP(T, beta), MP(T, C), ldc); }           \
+  void P##syrk_(const char* ul, const char* tr, const int* n, const int* k, const void* alpha, const void* A, const int* lda,   \
+                const void* beta, void* C, const int* ldc, size_t, size_t) {                                                   \
+    f_syrk<T>(UP "SYRK ", ul, tr, n, k, CP(T, alpha), CP(T, A), lda, CP(T, beta), MP(T, C), ldc); }                             \
+  void P##herk_(const char* ul, const char* tr, const int* n, const int* k, const R* alpha, const void* A, const int* lda,      \
+                const R* beta, void* C, const int* ldc, size_t, size_t) {                                                      \
+    f_herk<T>(UP "HERK ", ul, tr, n, k, alpha, CP(T, A), lda, beta, MP(T, C), ldc); }                                           \
+  void P##trsm_(const char* sd, const char* ul, const char* ta, const char* dg, const int* m, const int* n, const void* alpha,  \
+                const void* A, const int* lda, void* B, const int* ldb, size_t, size_t, size_t, size_t) {                       \
+    f_trxm<T>(UP "TRSM ", true, sd, ul, ta, dg, m, n, CP(T, alpha), CP(T, A), lda, MP(T, B), ldb); }                            \
+  void P##trmm_(const char* sd, const char* ul, const char* ta, const char* dg, const int* m, const int* n, const void* alpha,  \
+                const void* A, const int* lda, void* B, const int* ldb, size_t, size_t, size_t, size_t) {                       \
+    f_trxm<T>(UP "TRMM ", false, sd, ul, ta, dg, m, n, CP(T, alpha), CP(T, A), lda, MP(T, B), ldb); }                           \
+  void P##getrf_(const int* m, const int* n, void* A, const int* lda, int* ipiv, int* info) { f_getrf<T>(UP "GETRF", m, n, MP(T, A), lda, ipiv, info); } \
+  void P##potrf_(const char* ul, const int* n, void* A, const int* lda, int* info, size_t) { f_potrf<T>(UP "POTRF", ul, n, MP(T, A), lda, info); }
+
+CPLX_API(c, cfloat, float, "C")
+CPLX_API(z, cdouble, double, "Z")
+}  // extern "C"

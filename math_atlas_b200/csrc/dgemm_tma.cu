@@ -84,7 +84,8 @@ template <bool A_KMAJOR, bool B_KMAJOR>
 __global__ void __launch_bounds__(THREADS, 1)
 dgemm_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                  double* __restrict__ C, size_t ldc, int M, int N, int K, double alpha, double beta,
-                 int cmode, int tiles_m, int tiles_n) {
+                 int cmode, int tiles_m, int tiles_n, const int* __restrict__ abort_flag) {
+  if (abort_flag && *abort_flag) return;  // POTRF stop-at-first-failure (uniform for the whole grid)
   // ---- tile coordinates (grouped rasterisation) ----
   const int pid = blockIdx.x;
   const int in_group = GROUP_M * tiles_n;
@@ -231,7 +232,7 @@ bool make_map(CUtensorMap* tm, const double* ptr, size_t rows, size_t cols, size
 
 template <bool AK, bool BK_>
 void launch(const CUtensorMap& ta, const CUtensorMap& tb, double* C, size_t ldc, int M, int N, int K, double alpha,
-            double beta, int cmode) {
+            double beta, int cmode, const int* abort_flag) {
   static bool attr_set = false;
   if (!attr_set) {
     AB_CUDA_CHECK(cudaFuncSetAttribute(dgemm_tma_kernel<AK, BK_>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
@@ -239,7 +240,7 @@ void launch(const CUtensorMap& ta, const CUtensorMap& tb, double* C, size_t ldc,
   }
   const int tiles_m = (M + BM - 1) / BM, tiles_n = (N + BN - 1) / BN;
   dgemm_tma_kernel<AK, BK_><<<tiles_m * tiles_n, THREADS, SMEM_BYTES, current_stream()>>>(
-      ta, tb, C, ldc, M, N, K, alpha, beta, cmode, tiles_m, tiles_n);
+      ta, tb, C, ldc, M, N, K, alpha, beta, cmode, tiles_m, tiles_n, abort_flag);
   count_launch();
   AB_CUDA_CHECK(cudaGetLastError());
 }
@@ -256,7 +257,7 @@ bool dgemm_tma_eligible(int M, int N, int K, const double* A, size_t lda, const 
 }
 
 bool dgemm_tma(int ta, int tb, int M, int N, int K, double alpha, const double* A, size_t lda, const double* B,
-               size_t ldb, double beta, double* C, size_t ldc, int cmode) {
+               size_t ldb, double beta, double* C, size_t ldc, int cmode, const int* abort_flag) {
   if (!dgemm_tma_eligible(M, N, K, A, lda, B, ldb)) return false;
   CUtensorMap mA, mB;
   bool ok;
@@ -266,10 +267,10 @@ bool dgemm_tma(int ta, int tb, int M, int N, int K, double alpha, const double* 
   // op(B) is K x N.  !tb: stored K x N (K-major) else stored N x K (n contiguous).
   ok = tb ? make_map(&mB, B, N, K, ldb, 16, BK) : make_map(&mB, B, K, N, ldb, BK, BN);
   if (!ok) return false;
-  if (ta) { if (!tb) launch<true, true>(mA, mB, C, ldc, M, N, K, alpha, beta, cmode);
-            else     launch<true, false>(mA, mB, C, ldc, M, N, K, alpha, beta, cmode); }
-  else    { if (!tb) launch<false, true>(mA, mB, C, ldc, M, N, K, alpha, beta, cmode);
-            else     launch<false, false>(mA, mB, C, ldc, M, N, K, alpha, beta, cmode); }
+  if (ta) { if (!tb) launch<true, true>(mA, mB, C, ldc, M, N, K, alpha, beta, cmode, abort_flag);
+            else     launch<true, false>(mA, mB, C, ldc, M, N, K, alpha, beta, cmode, abort_flag); }
+  else    { if (!tb) launch<false, true>(mA, mB, C, ldc, M, N, K, alpha, beta, cmode, abort_flag);
+            else     launch<false, false>(mA, mB, C, ldc, M, N, K, alpha, beta, cmode, abort_flag); }
   return true;
 }
 

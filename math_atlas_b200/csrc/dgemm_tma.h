@@ -7,5 +7,5 @@ bool dgemm_tma_eligible(int M, int N, int K, const double* A, size_t lda, const 
 // C(cmode triangle) = alpha*op(A)*op(B) + beta*C on device pointers; ta/tb = 1 for transposed operands.
 // Returns false (nothing launched) when not eligible.
 bool dgemm_tma(int ta, int tb, int M, int N, int K, double alpha, const double* A, size_t lda, const double* B,
-               size_t ldb, double beta, double* C, size_t ldc, int cmode);
+               size_t ldb, double beta, double* C, size_t ldc, int cmode, const int* abort_flag = nullptr);
 }  // namespace ab

@@ -26,6 +26,7 @@ struct GemmP {
   int cmode;  // CMode: which triangle of C is written
   int herk;   // force Im(C(i,i)) = 0 (HERK semantics, reference ATL_ipsyrk.c:478-481)
   int triA, triB;  // TRI_* masks for a triangular operand (TRMM)
+  const int* abort_flag;  // if non-null and *abort_flag != 0 the kernel does nothing (POTRF stop-at-failure)
 };
 
 template <typename T>
@@ -47,6 +48,7 @@ __global__ void __launch_bounds__(GG_THREADS) gemm_generic_kernel(const GemmP<T>
   __shared__ T Bs[GG_BK][GG_BN + PAD];
 
   const int m0 = blockIdx.x * GG_BM, n0 = blockIdx.y * GG_BN;
+  if (p.abort_flag && *p.abort_flag) return;
   if (p.cmode == C_UPPER && m0 > n0 + GG_BN - 1) return;
   if (p.cmode == C_LOWER && n0 > m0 + GG_BM - 1) return;
 

@@ -1,0 +1,470 @@
+// Recursive LU (partial pivoting) and Cholesky on device pointers, plus the row-interchange kernel.
+//
+// Host-side structure follows the reference exactly (Clint/atlas-lp.base):
+//   ATL_getrfC :1497-1617   getrfC(left) ; laswp(right) ; trsm(L,L,N,U) ; gemm(-1,+1) ; getrfC(right-bottom) ;
+//                           ipiv += Nleft ; laswp(left)
+//   ATL_potrfL :909-968     potrfL(left) ; trsm(R,L,T,N) ; syrk/herk(L,N,-1,+1) ; potrfL(right)
+//   ATL_potrfU :675-733     potrfU(left) ; trsm(L,U,T,N) ; syrk/herk(U,T,-1,+1) ; potrfU(right)
+// but the whole recursion is only kernel launches on one stream: pivots, info and the
+// "stop at the first non-positive pivot" condition live in device memory, so the host never
+// waits inside a factorisation.
+//
+// Leaves:
+//   getf2_panel_kernel  replaces ATL_Xgetf2 / LU1 / LU2 (:5204-5379, :1301): a cooperative
+//       multi-CTA kernel, one thread per matrix row, the row's <=32 panel entries in registers.
+//       Per column: block arg-max (iamax semantics: first index of strictly larger |x|, |re|+|im|
+//       for complex), candidates published, one grid barrier, every CTA picks the winner, the two
+//       row owners exchange rows, everybody scales by the reciprocal (if |piv| >= SAFMIN, else
+//       divides, :5255) and applies the rank-1 update to its registers.
+//   potf2_kernel        replaces ATL_potrf2 / potrfL_{2,3,4} (:737-905): one CTA, block in shared memory.
+//   laswp_kernel        replaces ATL_laswp (:1053): one thread per column, pivots applied in order.
+#include "ab_api.h"
+#include <cfloat>
+#include <type_traits>
+
+namespace ab {
+
+// ------------------------------------------------------------------------------------- laswp
+template <typename T>
+__global__ void laswp_kernel(int N, T* __restrict__ A, size_t lda, int K1, int K2, const int* __restrict__ piv, int inci) {
+  const int col = blockIdx.x * blockDim.x + threadIdx.x;
+  if (col >= N) return;
+  T* a = A + (size_t)col * lda;
+  if (inci >= 0) {
+    for (int i = K1; i < K2; i++) {
+      const int ip = piv[(size_t)i * inci];
+      if (ip != i) { T t = a[i]; a[i] = a[ip]; a[ip] = t; }
+    }
+  } else {
+    // reference: piv -= (K2-1)*inci ; i runs K2-1 .. K1 reading consecutive entries
+    const int* p = piv - (ptrdiff_t)(K2 - 1) * inci;
+    for (int i = K2 - 1; i >= K1; i--, p += inci) {
+      const int ip = *p;
+      if (ip != i) { T t = a[i]; a[i] = a[ip]; a[ip] = t; }
+    }
+  }
+}
+
+template <typename T>
+void laswp(int N, T* A, size_t lda, int K1, int K2, const int* d_piv, int inci) {
+  if (N <= 0 || K2 <= K1) return;
+  const int threads = 128;
+  laswp_kernel<T><<<(N + threads - 1) / threads, threads, 0, current_stream()>>>(N, A, lda, K1, K2, d_piv, inci);
+  count_launch();
+  AB_CUDA_CHECK(cudaGetLastError());
+}
+
+__global__ void ipiv_add_kernel(int* piv, int n, int add) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) piv[i] += add;
+}
+__global__ void info_merge_kernel(int* info, const int* sub, int add) {
+  // ierr = first failure: keep an earlier one, else take the sub-problem's (shifted)
+  if (*info == 0 && *sub != 0) *info = *sub + add;
+}
+
+// ------------------------------------------------------------------------------------- LU panel
+template <typename T> struct Safmin;
+template <> struct Safmin<float>   { static __device__ float v()  { return FLT_MIN; } };
+template <> struct Safmin<double>  { static __device__ double v() { return DBL_MIN; } };
+template <> struct Safmin<float2>  { static __device__ float v()  { return FLT_MIN; } };
+template <> struct Safmin<double2> { static __device__ double v() { return DBL_MIN; } };
+
+template <typename T> __device__ __forceinline__ T p_recip(T d) { return ST<T>::one() / d; }
+template <> __device__ __forceinline__ float2 p_recip<float2>(float2 a) {
+  float t, d;
+  if (fabsf(a.x) >= fabsf(a.y)) { t = a.y / a.x; d = a.x + a.y * t; return make_float2(1.f / d, -t / d); }
+  t = a.x / a.y; d = a.x * t + a.y; return make_float2(t / d, -1.f / d);
+}
+template <> __device__ __forceinline__ double2 p_recip<double2>(double2 a) {
+  double t, d;
+  if (fabs(a.x) >= fabs(a.y)) { t = a.y / a.x; d = a.x + a.y * t; return make_double2(1. / d, -t / d); }
+  t = a.x / a.y; d = a.x * t + a.y; return make_double2(t / d, -1. / d);
+}
+
+constexpr int PNL_THREADS = 256;
+
+__device__ __forceinline__ void grid_barrier(unsigned* counter, unsigned target) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    atomicAdd(counter, 1u);
+    volatile unsigned* vc = counter;
+    while (*vc < target) { }
+    __threadfence();
+  }
+  __syncthreads();
+}
+
+// W = panel width capacity (columns held per thread), RPT = rows per thread.
+// ws layout (per column step j, distinct slots so there is no reuse hazard inside a launch):
+//   cval[j][nb]  (real)   candidate magnitude of block b   (-1 if the block has no candidate row)
+//   crow[j][nb]  (int)    candidate row
+//   crows[j][nb][W] (T)   candidate row contents
+//   jrow[j][W]   (T)      contents of row j before the swap
+template <typename T, int W, int RPT>
+__global__ void __launch_bounds__(PNL_THREADS)
+getf2_panel_kernel(int M, int w, T* __restrict__ A, size_t lda, int* __restrict__ ipiv, int* __restrict__ info,
+                   unsigned* __restrict__ counter, typename ST<T>::real* __restrict__ cval, int* __restrict__ crow,
+                   T* __restrict__ crows, T* __restrict__ jrow) {
+  using S = ST<T>;
+  using R = typename S::real;
+  const int nb = gridDim.x, b = blockIdx.x, tid = threadIdx.x;
+  const int lane = tid & 31, wid = tid >> 5;
+  __shared__ R s_val[PNL_THREADS / 32];
+  __shared__ int s_row[PNL_THREADS / 32];
+  __shared__ int s_win_row, s_win_blk;
+  __shared__ T s_prow[W], s_jrow[W];
+
+  // rows owned by this thread: r = (b*RPT + q)*PNL_THREADS + tid   (coalesced per q)
+  T a[RPT][W];
+  int rows[RPT];
+#pragma unroll
+  for (int q = 0; q < RPT; q++) {
+    rows[q] = (b * RPT + q) * PNL_THREADS + tid;
+#pragma unroll
+    for (int c = 0; c < W; c++)
+      a[q][c] = (rows[q] < M && c < w) ? A[(size_t)rows[q] + (size_t)c * lda] : S::zero();
+  }
+  const int MN = min(M, w);
+
+#pragma unroll
+  for (int j = 0; j < W; j++) {
+    if (j < MN) {
+      // ---- 1. block-local pivot candidate among rows >= j
+      R best = (R)-1; int brow = 0x7fffffff;
+#pragma unroll
+      for (int q = 0; q < RPT; q++) {
+        if (rows[q] >= j && rows[q] < M) {
+          const R v = S::abs1(a[q][j]);
+          if (v > best || (v == best && rows[q] < brow)) { best = v; brow = rows[q]; }
+        }
+      }
+#pragma unroll
+      for (int off = 16; off > 0; off >>= 1) {
+        const R ov = __shfl_xor_sync(0xffffffffu, best, off);
+        const int orow = __shfl_xor_sync(0xffffffffu, brow, off);
+        if (ov > best || (ov == best && orow < brow)) { best = ov; brow = orow; }
+      }
+      if (lane == 0) { s_val[wid] = best; s_row[wid] = brow; }
+      __syncthreads();
+      if (wid == 0) {
+        R v = (lane < PNL_THREADS / 32) ? s_val[lane] : (R)-1;
+        int r = (lane < PNL_THREADS / 32) ? s_row[lane] : 0x7fffffff;
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) {
+          const R ov = __shfl_xor_sync(0xffffffffu, v, off);
+          const int orow = __shfl_xor_sync(0xffffffffu, r, off);
+          if (ov > v || (ov == v && orow < r)) { v = ov; r = orow; }
+        }
+        if (lane == 0) {
+          s_win_row = r;
+          cval[(size_t)j * nb + b] = v;
+          crow[(size_t)j * nb + b] = r;
+        }
+      }
+      __syncthreads();
+      // ---- 2. publish the candidate row's contents and row j's contents
+      {
+        const int cr = s_win_row;
+#pragma unroll
+        for (int q = 0; q < RPT; q++) {
+          if (rows[q] == cr) {
+            T* dst = crows + ((size_t)j * nb + b) * W;
+#pragma unroll
+            for (int c = 0; c < W; c++) dst[c] = a[q][c];
+          }
+          if (rows[q] == j) {
+            T* dst = jrow + (size_t)j * W;
+#pragma unroll
+            for (int c = 0; c < W; c++) dst[c] = a[q][c];
+          }
+        }
+      }
+      // ---- 3. grid barrier, 4. global winner (max value, lowest row)
+      grid_barrier(counter, (unsigned)(j + 1) * (unsigned)nb);
+      if (wid == 0) {
+        R v = (R)-1; int r = 0x7fffffff, wb = 0;
+        for (int k = lane; k < nb; k += 32) {
+          const R ov = __ldcg(&cval[(size_t)j * nb + k]);
+          const int orow = __ldcg(&crow[(size_t)j * nb + k]);
+          if (ov > v || (ov == v && orow < r)) { v = ov; r = orow; wb = k; }
+        }
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) {
+          const R ov = __shfl_xor_sync(0xffffffffu, v, off);
+          const int orow = __shfl_xor_sync(0xffffffffu, r, off);
+          const int owb = __shfl_xor_sync(0xffffffffu, wb, off);
+          if (ov > v || (ov == v && orow < r)) { v = ov; r = orow; wb = owb; }
+        }
+        // no comparable candidate (column is all NaN): iamax returns the first index, i.e. row j
+        if (lane == 0) { s_win_row = (r == 0x7fffffff) ? j : r; s_win_blk = (r == 0x7fffffff) ? -1 : wb; }
+      }
+      __syncthreads();
+      const int p = s_win_row;
+      if (tid < W) {
+        s_jrow[tid] = __ldcg(&jrow[(size_t)j * W + tid]);
+        s_prow[tid] = (s_win_blk < 0) ? s_jrow[tid] : __ldcg(&crows[((size_t)j * nb + s_win_blk) * W + tid]);
+      }
+      __syncthreads();
+      const T piv = s_prow[j];
+      const bool nonzero = !S::is_zero(piv);
+      if (b == 0 && tid == 0) {
+        ipiv[j] = p;
+        if (!nonzero && *info == 0) *info = j + 1;
+      }
+      // ---- 6. row exchange (only when the pivot is non-zero, like LU1), 7. scale + rank-1 update
+      T rcp = S::zero();
+      bool use_rcp = false;
+      if (nonzero) { use_rcp = S::abs1(piv) >= Safmin<T>::v(); if (use_rcp) rcp = p_recip<T>(piv); }
+#pragma unroll
+      for (int q = 0; q < RPT; q++) {
+        if (nonzero && p != j) {
+          if (rows[q] == p) {
+#pragma unroll
+            for (int c = 0; c < W; c++) a[q][c] = s_jrow[c];
+          } else if (rows[q] == j) {
+#pragma unroll
+            for (int c = 0; c < W; c++) a[q][c] = s_prow[c];
+          }
+        }
+        if (rows[q] > j && rows[q] < M) {
+          T l = a[q][j];
+          if (nonzero) {
+            if (use_rcp) l = S::mul(l, rcp);
+            else l = S::mul(l, p_recip<T>(piv));   // |piv| < SAFMIN: the reference divides
+            a[q][j] = l;
+          }
+          // the rank-1 update uses row j AFTER the swap: that is the pivot row if swapped, else row j itself
+#pragma unroll
+          for (int c = j + 1; c < W; c++) {
+            const T u = (nonzero ? s_prow[c] : s_jrow[c]);
+            a[q][c] = S::sub(a[q][c], S::mul(l, u));
+          }
+        }
+      }
+      __syncthreads();   // s_prow / s_jrow are rewritten next step
+    }
+  }
+#pragma unroll
+  for (int q = 0; q < RPT; q++)
+    if (rows[q] < M) {
+#pragma unroll
+      for (int c = 0; c < W; c++)
+        if (c < w) A[(size_t)rows[q] + (size_t)c * lda] = a[q][c];
+    }
+}
+
+template <typename T> struct PanelW { static constexpr int W = 32; };
+template <> struct PanelW<double2> { static constexpr int W = 16; };
+
+template <typename T, int W, int RPT>
+static long panel_capacity() {   // rows that fit co-resident for this variant
+  static long cap = -1;
+  if (cap < 0) {
+    int dev, sms, per_sm;
+    AB_CUDA_CHECK(cudaGetDevice(&dev));
+    AB_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    AB_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, getf2_panel_kernel<T, W, RPT>, PNL_THREADS, 0));
+    cap = (long)sms * per_sm * PNL_THREADS * RPT;
+  }
+  return cap;
+}
+
+template <typename T, int W, int RPT>
+static void panel_launch(int M, int w, T* A, size_t lda, int* d_ipiv, int* d_info) {
+  using R = typename ST<T>::real;
+  const int nb = (M + PNL_THREADS * RPT - 1) / (PNL_THREADS * RPT);
+  // workspace: counter | cval | crow | crows | jrow
+  const size_t steps = (size_t)min(M, w);
+  size_t off = 256;
+  const size_t o_cval = off; off += ((steps * nb * sizeof(R) + 255) / 256) * 256;
+  const size_t o_crow = off; off += ((steps * nb * sizeof(int) + 255) / 256) * 256;
+  const size_t o_crows = off; off += ((steps * nb * W * sizeof(T) + 255) / 256) * 256;
+  off += ((steps * W * sizeof(T) + 255) / 256) * 256;
+  char* ws = static_cast<char*>(workspace(off, 1));
+  AB_CUDA_CHECK(cudaMemsetAsync(ws, 0, 256, current_stream()));
+  unsigned* counter = reinterpret_cast<unsigned*>(ws);
+  R* cval = reinterpret_cast<R*>(ws + o_cval);
+  int* crow = reinterpret_cast<int*>(ws + o_crow);
+  T* crows = reinterpret_cast<T*>(ws + o_crows);
+  T* jrow = reinterpret_cast<T*>(ws + o_crows + ((steps * nb * W * sizeof(T) + 255) / 256) * 256);
+  void* args[] = {&M, &w, &A, &lda, &d_ipiv, &d_info, &counter, &cval, &crow, &crows, &jrow};
+  AB_CUDA_CHECK(cudaLaunchCooperativeKernel((void*)getf2_panel_kernel<T, W, RPT>, dim3(nb), dim3(PNL_THREADS), args, 0,
+                                            current_stream()));
+  count_launch();
+}
+
+// widest leaf panel whose M rows fit co-resident (narrower panels hold more rows per thread)
+template <typename T>
+static int panel_width_for(int M) {
+  constexpr int W = PanelW<T>::W;
+  if (M <= panel_capacity<T, W, 1>()) return W;
+  if (M <= panel_capacity<T, W / 2, 2>()) return W / 2;
+  if (M <= panel_capacity<T, W / 4, 4>()) return W / 4;
+  fprintf(stderr, "atlas_b200: getrf with %d rows exceeds the co-resident panel capacity of this GPU\n", M);
+  abort();
+}
+
+// factor an M x w panel, w <= leaf_w (the width panel_width_for() chose for the whole factorisation)
+template <typename T>
+static void getf2_panel(int M, int w, int leaf_w, T* A, size_t lda, int* d_ipiv, int* d_info) {
+  constexpr int W = PanelW<T>::W;
+  if (leaf_w == W) panel_launch<T, W, 1>(M, w, A, lda, d_ipiv, d_info);
+  else if (leaf_w == W / 2) panel_launch<T, W / 2, 2>(M, w, A, lda, d_ipiv, d_info);
+  else panel_launch<T, W / 4, 4>(M, w, A, lda, d_ipiv, d_info);
+}
+
+template <typename T>
+static void getrf_rec(int M, int N, T* A, size_t lda, int* d_ipiv, int* d_info, int* d_sub, int leaf_w) {
+  using S = ST<T>;
+  const int MN = min(M, N);
+  if (MN <= 0) return;
+  if (N <= leaf_w) {
+    // leaf: d_sub is a scratch info for the panel, merged by the caller
+    getf2_panel<T>(M, N, leaf_w, A, lda, d_ipiv, d_info);
+    return;
+  }
+  // Nleft = MN/2 rounded down to a multiple of the leaf width (the reference rounds to its tuned
+  // ATL_VWipgen_100LCMMN, atlas-lp.base:1535-1538)
+  int Nleft = MN >> 1;
+  if (Nleft > leaf_w) Nleft = (Nleft / leaf_w) * leaf_w;
+  if (Nleft < 1) Nleft = 1;
+  const int Nright = N - Nleft;
+  T* Ac = A + (size_t)Nleft * lda;
+  T* An = Ac + Nleft;
+  getrf_rec<T>(M, Nleft, A, lda, d_ipiv, d_info, d_sub, leaf_w);
+  laswp<T>(Nright, Ac, lda, 0, Nleft, d_ipiv, 1);
+  trsm<T>(Left, Lower, NoTrans, Unit, Nleft, Nright, S::one(), A, lda, Ac, lda);
+  gemm<T>(NoTrans, NoTrans, M - Nleft, Nright, Nleft, S::from_real(-1), A + Nleft, lda, Ac, lda, S::one(), An, lda);
+  if (M - Nleft > 0) {
+    AB_CUDA_CHECK(cudaMemsetAsync(d_sub, 0, sizeof(int), current_stream()));
+    int* d_sub2 = d_sub + 1;   // scratch chain: one int per recursion depth
+    getrf_rec<T>(M - Nleft, Nright, An, lda, d_ipiv + Nleft, d_sub, d_sub2, leaf_w);
+    const int nr = MN - Nleft;
+    if (nr > 0) {
+      ipiv_add_kernel<<<(nr + 255) / 256, 256, 0, current_stream()>>>(d_ipiv + Nleft, nr, Nleft);
+      count_launch();
+    }
+    info_merge_kernel<<<1, 1, 0, current_stream()>>>(d_info, d_sub, Nleft);
+    count_launch();
+    laswp<T>(Nleft, A, lda, Nleft, MN, d_ipiv, 1);
+  }
+}
+
+template <typename T>
+void getrf(int M, int N, T* A, size_t lda, int* d_ipiv, int* d_info) {
+  AB_CUDA_CHECK(cudaMemsetAsync(d_info, 0, sizeof(int), current_stream()));
+  if (M <= 0 || N <= 0) return;
+  int* d_sub = static_cast<int*>(workspace(64 * sizeof(int), 2));
+  getrf_rec<T>(M, N, A, lda, d_ipiv, d_info, d_sub, panel_width_for<T>(M));
+}
+
+// ------------------------------------------------------------------------------------- Cholesky leaf
+constexpr int PF_NB = 32;
+
+template <typename T>
+__global__ void __launch_bounds__(PF_NB * PF_NB / 4)
+potf2_kernel(int upper, int n, T* __restrict__ A, size_t lda, int* __restrict__ info, int info_off) {
+  using S = ST<T>;
+  using R = typename S::real;
+  if (*info != 0) return;
+  // work on L (lower); for Upper load the conjugate transpose so the same code runs
+  __shared__ T Ls[PF_NB][PF_NB + 1];
+  __shared__ int s_fail;
+  const int tid = threadIdx.x, nt = blockDim.x;
+  if (tid == 0) s_fail = 0;
+  for (int idx = tid; idx < n * n; idx += nt) {
+    const int i = idx % n, j = idx / n;   // i >= j part is used
+    if (i >= j) {
+      T v = upper ? S::conj(A[(size_t)j + (size_t)i * lda]) : A[(size_t)i + (size_t)j * lda];
+      Ls[i][j] = v;
+    }
+  }
+  __syncthreads();
+  for (int j = 0; j < n; j++) {
+    // diagonal: real part only (the reference treats Im(diag) as zero)
+    R d;
+    if constexpr (S::cplx) d = Ls[j][j].x; else d = Ls[j][j];
+    if (!(d > (R)0)) {
+      if (tid == 0) { s_fail = j + 1; if constexpr (S::cplx) Ls[j][j] = S::from_real(d); }
+      __syncthreads();
+      break;
+    }
+    const R sd = sqrt(d);
+    __syncthreads();
+    if (tid == 0) Ls[j][j] = S::from_real(sd);
+    for (int i = j + 1 + tid; i < n; i += nt) {
+      T v = Ls[i][j];
+      if constexpr (S::cplx) { v.x /= sd; v.y /= sd; } else v /= sd;
+      Ls[i][j] = v;
+    }
+    __syncthreads();
+    // trailing update: L[i][k] -= L[i][j] * conj(L[k][j]) for j < k <= i
+    const int rem = n - j - 1;
+    for (int idx = tid; idx < rem * rem; idx += nt) {
+      const int i = j + 1 + idx % rem, k = j + 1 + idx / rem;
+      if (k <= i) Ls[i][k] = S::sub(Ls[i][k], S::mul(Ls[i][j], S::conj(Ls[k][j])));
+    }
+    __syncthreads();
+  }
+  const int fail = s_fail;
+  // write back the columns factored so far (all of them when fail == 0); like the reference, the
+  // failing diagonal entry holds the non-positive value and later columns are left as they were
+  const int ncols = fail ? fail : n;
+  for (int idx = tid; idx < n * n; idx += nt) {
+    const int i = idx % n, j = idx / n;
+    if (i >= j && (j < ncols - (fail ? 1 : 0) || (fail && j == fail - 1 && i == j))) {
+      T v = Ls[i][j];
+      if (upper) A[(size_t)j + (size_t)i * lda] = S::conj(v); else A[(size_t)i + (size_t)j * lda] = v;
+    }
+  }
+  if (fail && tid == 0) *info = fail + info_off;
+}
+
+template <typename T>
+static void potrf_rec(int uplo, int N, T* A, size_t lda, int* d_info, int off) {
+  using S = ST<T>;
+  using R = typename S::real;
+  if (N <= 0) return;
+  if (N <= PF_NB) {
+    potf2_kernel<T><<<1, PF_NB * PF_NB / 4, 0, current_stream()>>>(uplo == Upper, N, A, lda, d_info, off);
+    count_launch();
+    AB_CUDA_CHECK(cudaGetLastError());
+    return;
+  }
+  int Nleft = N >> 1;
+  if (Nleft > PF_NB) Nleft = (Nleft / PF_NB) * PF_NB;
+  const int Nright = N - Nleft;
+  potrf_rec<T>(uplo, Nleft, A, lda, d_info, off);
+  const int tr = S::cplx ? ConjTrans : TransT;
+  if (uplo == Lower) {
+    T* Ar = A + Nleft;
+    T* An = Ar + (size_t)Nleft * lda;
+    trsm<T>(Right, Lower, tr, NonUnit, Nright, Nleft, S::one(), A, lda, Ar, lda, d_info);
+    if constexpr (S::cplx) herk<T>(Lower, NoTrans, Nright, Nleft, (R)-1, Ar, lda, (R)1, An, lda, d_info);
+    else syrk<T>(Lower, NoTrans, Nright, Nleft, S::from_real(-1), Ar, lda, S::one(), An, lda, d_info);
+    potrf_rec<T>(uplo, Nright, An, lda, d_info, off + Nleft);
+  } else {
+    T* Ac = A + (size_t)Nleft * lda;
+    T* An = Ac + Nleft;
+    trsm<T>(Left, Upper, tr, NonUnit, Nleft, Nright, S::one(), A, lda, Ac, lda, d_info);
+    if constexpr (S::cplx) herk<T>(Upper, ConjTrans, Nright, Nleft, (R)-1, Ac, lda, (R)1, An, lda, d_info);
+    else syrk<T>(Upper, TransT, Nright, Nleft, S::from_real(-1), Ac, lda, S::one(), An, lda, d_info);
+    potrf_rec<T>(uplo, Nright, An, lda, d_info, off + Nleft);
+  }
+}
+
+template <typename T>
+void potrf(int uplo, int N, T* A, size_t lda, int* d_info) {
+  AB_CUDA_CHECK(cudaMemsetAsync(d_info, 0, sizeof(int), current_stream()));
+  potrf_rec<T>(uplo, N, A, lda, d_info, 0);
+}
+
+#define AB_INST(T)                                                    \
+  template void laswp<T>(int, T*, size_t, int, int, const int*, int); \
+  template void getrf<T>(int, int, T*, size_t, int*, int*);           \
+  template void potrf<T>(int, int, T*, size_t, int*);
+AB_INST(float) AB_INST(double) AB_INST(float2) AB_INST(double2)
+
+}  // namespace ab

@@ -1,0 +1,296 @@
+// Level-3 BLAS drivers on device pointers: GEMM dispatch, SYRK/HERK, TRMM, TRSM.
+//
+// Structure mirrors the reference (everything off-diagonal is GEMM, the triangle is handled by
+// recursion down to a small base block):
+//   ATL_Xgemm / ATL_Xammm     Clint/atlas-ammm.base:17707-17806   -> gemm<T>()
+//   ATL_Xsyrk / ATL_Xherk     Clint/l3micro.base:2358-2760         -> syrk<T>() / herk<T>()  (GEMM core + C-triangle mask)
+//   ATL_Xtrmm, trmm_recL/R    Clint/trmm-micro.base:1942-2157      -> trmm<T>()  (rec; gemm; rec ordering for in-place safety)
+//   ATL_Xtrsm, trsm_recL/R    Clint/trsm-micro.base:200-424        -> trsm<T>()  (rec(NL); gemm(-1, alpha); rec(NR, 1))
+//   ATL_utrsm*/ATL_ntrsm*     Clint/trsm-micro.base:1372-2023, Students/trsm-nano.base:206-1650
+//                                                                  -> trsm_base_kernel (one thread per right-hand side,
+//                                                                     triangle in shared memory, all flags folded into the load)
+#include "ab_api.h"
+#include "gemm_generic.cuh"
+#include "dgemm_tma.h"
+#include <type_traits>
+
+namespace ab {
+
+static inline bool is_tr(int t) { return t == TransT || t == ConjTrans; }
+static inline bool is_cj(int t) { return t == ConjTrans || t == AtlasConj; }
+
+// ------------------------------------------------------------------------------------- GEMM
+template <typename T>
+static void gemm_flags(int ta, int ca, int tb, int cb, int M, int N, int K, T alpha, const T* A, size_t lda, const T* B,
+                       size_t ldb, T beta, T* C, size_t ldc, int cmode, int herk, const int* abort_flag) {
+  using S = ST<T>;
+  if (M <= 0 || N <= 0) return;
+  GemmP<T> p{M, N, K, A, lda, ta, S::cplx ? ca : 0, B, ldb, tb, S::cplx ? cb : 0, alpha, beta, C, ldc, cmode, herk, 0, 0, abort_flag};
+  if (S::is_zero(alpha) || K <= 0) {
+    // C <- beta*C only; beta==0 writes explicit zeros, A and B are not referenced
+    // (reference atlas-ammm.base:17729-17741)
+    if (S::is_one(beta) && !herk) return;
+    p.K = 0; p.alpha = S::zero();
+    gemm_generic_launch(p);
+    return;
+  }
+  if constexpr (std::is_same<T, double>::value) {
+    if ((double)M * N * K >= 262144.0 && !herk &&
+        dgemm_tma(ta, tb, M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, cmode, abort_flag))
+      return;
+  }
+  gemm_generic_launch(p);
+}
+
+template <typename T>
+void gemm(int TA, int TB, int M, int N, int K, T alpha, const T* A, size_t lda, const T* B, size_t ldb, T beta, T* C,
+          size_t ldc, const int* abort_flag) {
+  gemm_flags<T>(is_tr(TA), is_cj(TA), is_tr(TB), is_cj(TB), M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, C_FULL, 0, abort_flag);
+}
+
+// ------------------------------------------------------------------------------------- SYRK / HERK
+template <typename T>
+void syrk(int uplo, int trans, int N, int K, T alpha, const T* A, size_t lda, T beta, T* C, size_t ldc, const int* abort_flag) {
+  const int cm = (uplo == Upper) ? C_UPPER : C_LOWER;
+  if (!is_tr(trans)) gemm_flags<T>(0, 0, 1, 0, N, N, K, alpha, A, lda, A, lda, beta, C, ldc, cm, 0, abort_flag);  // A*A^T
+  else               gemm_flags<T>(1, 0, 0, 0, N, N, K, alpha, A, lda, A, lda, beta, C, ldc, cm, 0, abort_flag);  // A^T*A
+}
+
+template <typename T>
+void herk(int uplo, int trans, int N, int K, typename ST<T>::real alpha, const T* A, size_t lda, typename ST<T>::real beta,
+          T* C, size_t ldc, const int* abort_flag) {
+  using S = ST<T>;
+  const int cm = (uplo == Upper) ? C_UPPER : C_LOWER;
+  const T al = S::from_real(alpha), be = S::from_real(beta);
+  if (!is_tr(trans)) gemm_flags<T>(0, 0, 1, 1, N, N, K, al, A, lda, A, lda, be, C, ldc, cm, 1, abort_flag);  // A*A^H
+  else               gemm_flags<T>(1, 1, 0, 0, N, N, K, al, A, lda, A, lda, be, C, ldc, cm, 1, abort_flag);  // A^H*A
+}
+
+// split point of the triangle recursions: halves, kept on 128/32 multiples so sub-blocks stay
+// 16-byte aligned for the TMA GEMM path
+static inline int tri_split(int n, int base) {
+  int h;
+  if (n >= 512) h = ((n / 2 + 127) / 128) * 128;
+  else h = ((n / 2 + base - 1) / base) * base;
+  if (h >= n) h = n / 2;
+  if (h < 1) h = 1;
+  return h;
+}
+
+// ------------------------------------------------------------------------------------- TRMM
+constexpr int TRMM_NB = 256;
+
+template <typename T>
+static void trmm_base(int side, int uplo, int trans, int diag, int M, int N, T alpha, const T* A, size_t lda, T* B, size_t ldb) {
+  using S = ST<T>;
+  // out-of-place through the workspace: W <- B ; B <- alpha * op(tri(A)) * W   (or W * op(tri(A)))
+  T* W = static_cast<T*>(workspace(sizeof(T) * (size_t)M * (size_t)N, 0));
+  AB_CUDA_CHECK(cudaMemcpy2DAsync(W, sizeof(T) * (size_t)M, B, sizeof(T) * ldb, sizeof(T) * (size_t)M, N,
+                                  cudaMemcpyDeviceToDevice, current_stream()));
+  const int tri = TRI_ON | (uplo == Upper ? TRI_UPPER : 0) | (diag == Unit ? TRI_UNIT : 0);
+  GemmP<T> p{};
+  p.M = M; p.N = N; p.alpha = alpha; p.beta = S::zero(); p.C = B; p.ldc = ldb; p.cmode = C_FULL;
+  if (side == Left) {
+    p.K = M; p.A = A; p.lda = lda; p.ta = is_tr(trans); p.ca = S::cplx ? is_cj(trans) : 0; p.triA = tri;
+    p.B = W; p.ldb = (size_t)M; p.tb = 0; p.cb = 0;
+  } else {
+    p.K = N; p.A = W; p.lda = (size_t)M; p.ta = 0; p.ca = 0;
+    p.B = A; p.ldb = lda; p.tb = is_tr(trans); p.cb = S::cplx ? is_cj(trans) : 0; p.triB = tri;
+  }
+  gemm_generic_launch(p);
+}
+
+template <typename T>
+static void trmm_rec(int side, int uplo, int trans, int diag, int M, int N, T alpha, const T* A, size_t lda, T* B, size_t ldb) {
+  using S = ST<T>;
+  const int n = (side == Left) ? M : N;
+  if (n <= TRMM_NB) { trmm_base<T>(side, uplo, trans, diag, M, N, alpha, A, lda, B, ldb); return; }
+  const int n1 = tri_split(n, 32), n2 = n - n1;
+  const bool eff_lower = (uplo == Lower) != is_tr(trans);   // op(A) lower triangular?
+  const T* A11 = A;
+  const T* A22 = A + (size_t)n1 + (size_t)n1 * lda;
+  // the stored off-diagonal block: A21 (stored lower) or A12 (stored upper)
+  const T* Aoff = (uplo == Lower) ? A + n1 : A + (size_t)n1 * lda;
+  const T one = S::one();
+  if (side == Left) {
+    T* B1 = B; T* B2 = B + n1;
+    if (eff_lower) {   // B2 <- T22 B2 + T21 B1 ; B1 <- T11 B1
+      trmm_rec<T>(side, uplo, trans, diag, n2, N, alpha, A22, lda, B2, ldb);
+      gemm<T>(trans, NoTrans, n2, N, n1, alpha, Aoff, lda, B1, ldb, one, B2, ldb);
+      trmm_rec<T>(side, uplo, trans, diag, n1, N, alpha, A11, lda, B1, ldb);
+    } else {           // B1 <- T11 B1 + T12 B2 ; B2 <- T22 B2
+      trmm_rec<T>(side, uplo, trans, diag, n1, N, alpha, A11, lda, B1, ldb);
+      gemm<T>(trans, NoTrans, n1, N, n2, alpha, Aoff, lda, B2, ldb, one, B1, ldb);
+      trmm_rec<T>(side, uplo, trans, diag, n2, N, alpha, A22, lda, B2, ldb);
+    }
+  } else {
+    T* B1 = B; T* B2 = B + (size_t)n1 * ldb;
+    if (eff_lower) {   // B1 <- B1 T11 + B2 T21 ; B2 <- B2 T22
+      trmm_rec<T>(side, uplo, trans, diag, M, n1, alpha, A11, lda, B1, ldb);
+      gemm<T>(NoTrans, trans, M, n1, n2, alpha, B2, ldb, Aoff, lda, one, B1, ldb);
+      trmm_rec<T>(side, uplo, trans, diag, M, n2, alpha, A22, lda, B2, ldb);
+    } else {           // B2 <- B2 T22 + B1 T12 ; B1 <- B1 T11
+      trmm_rec<T>(side, uplo, trans, diag, M, n2, alpha, A22, lda, B2, ldb);
+      gemm<T>(NoTrans, trans, M, n2, n1, alpha, B1, ldb, Aoff, lda, one, B2, ldb);
+      trmm_rec<T>(side, uplo, trans, diag, M, n1, alpha, A11, lda, B1, ldb);
+    }
+  }
+}
+
+template <typename T>
+void trmm(int side, int uplo, int trans, int diag, int M, int N, T alpha, const T* A, size_t lda, T* B, size_t ldb) {
+  using S = ST<T>;
+  if (M <= 0 || N <= 0) return;
+  if (S::is_zero(alpha)) {  // B <- 0 (reference: gescal by alpha==0 writes zeros)
+    gemm_flags<T>(0, 0, 0, 0, M, N, 0, S::zero(), B, ldb, B, ldb, S::zero(), B, ldb, C_FULL, 0, nullptr);
+    return;
+  }
+  trmm_rec<T>(side, uplo, trans, diag, M, N, alpha, A, lda, B, ldb);
+}
+
+// ------------------------------------------------------------------------------------- TRSM
+constexpr int TS_NB = 32;     // base triangle size
+constexpr int TS_VEC = 64;    // right-hand sides (threads) per CTA
+
+template <typename T> __device__ __forceinline__ T s_recip(T d) { return ST<T>::one() / d; }
+template <> __device__ __forceinline__ float2 s_recip<float2>(float2 a) {  // Smith, like ATL_Xcplxinvert
+  float t, d;
+  if (fabsf(a.x) >= fabsf(a.y)) { t = a.y / a.x; d = a.x + a.y * t; return make_float2(1.f / d, -t / d); }
+  t = a.x / a.y; d = a.x * t + a.y; return make_float2(t / d, -1.f / d);
+}
+template <> __device__ __forceinline__ double2 s_recip<double2>(double2 a) {
+  double t, d;
+  if (fabs(a.x) >= fabs(a.y)) { t = a.y / a.x; d = a.x + a.y * t; return make_double2(1. / d, -t / d); }
+  t = a.x / a.y; d = a.x * t + a.y; return make_double2(t / d, -1. / d);
+}
+
+// Canonical problem per right-hand side: L y = alpha*b with L lower triangular n x n (n <= TS_NB).
+//   Left : vectors are the columns of B, Tm = op(A)
+//   Right: vectors are the rows of B,    Tm = op(A)^T
+// If Tm is upper triangular the index order is reversed (rev) so the solve is always forward.
+template <typename T>
+__global__ void __launch_bounds__(TS_VEC)
+trsm_base_kernel(int left, int tt /*Tm(i,l) = tt ? A[l+i*lda] : A[i+l*lda]*/, int cj, int unit, int rev, int n, int nvec,
+                 T alpha, const T* __restrict__ A, size_t lda, T* __restrict__ B, size_t ldb, const int* abort_flag) {
+  using S = ST<T>;
+  if (abort_flag && *abort_flag) return;
+  __shared__ T Ls[TS_NB][TS_NB + 1];
+  for (int idx = threadIdx.x; idx < TS_NB * TS_NB; idx += TS_VEC) {
+    const int i = idx / TS_NB, l = idx % TS_NB;   // canonical indices
+    T v = S::zero();
+    if (i < n && l <= i) {
+      const int ri = rev ? n - 1 - i : i, rl = rev ? n - 1 - l : l;
+      if (i == l && unit) v = S::one();
+      else {
+        v = tt ? A[(size_t)rl + (size_t)ri * lda] : A[(size_t)ri + (size_t)rl * lda];
+        if (cj) v = S::conj(v);
+      }
+    }
+    Ls[i][l] = v;
+  }
+  __syncthreads();
+  const int v = blockIdx.x * TS_VEC + threadIdx.x;
+  if (v >= nvec) return;
+  T* bp = left ? B + (size_t)v * ldb : B + v;
+  const size_t estride = left ? 1 : ldb;
+  T x[TS_NB];
+#pragma unroll
+  for (int i = 0; i < TS_NB; i++) {
+    if (i < n) {
+      const int ri = rev ? n - 1 - i : i;
+      x[i] = S::mul(alpha, bp[(size_t)ri * estride]);
+    } else x[i] = S::zero();
+  }
+#pragma unroll
+  for (int i = 0; i < TS_NB; i++) {
+    if (i < n) {
+      T t = x[i];
+#pragma unroll
+      for (int l = 0; l < i; l++) t = S::sub(t, S::mul(Ls[i][l], x[l]));
+      if (!unit) t = S::mul(t, s_recip<T>(Ls[i][i]));
+      x[i] = t;
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < TS_NB; i++) {
+    if (i < n) {
+      const int ri = rev ? n - 1 - i : i;
+      bp[(size_t)ri * estride] = x[i];
+    }
+  }
+}
+
+template <typename T>
+static void trsm_base(int side, int uplo, int trans, int diag, int M, int N, T alpha, const T* A, size_t lda, T* B,
+                      size_t ldb, const int* abort_flag) {
+  using S = ST<T>;
+  const int left = (side == Left);
+  const int n = left ? M : N, nvec = left ? N : M;
+  const int tt = left ? is_tr(trans) : !is_tr(trans);
+  const bool tm_lower = (uplo == Lower) != (tt != 0);
+  const int grid = (nvec + TS_VEC - 1) / TS_VEC;
+  trsm_base_kernel<T><<<grid, TS_VEC, 0, current_stream()>>>(left, tt, S::cplx ? is_cj(trans) : 0, diag == Unit, !tm_lower, n, nvec,
+                                                            alpha, A, lda, B, ldb, abort_flag);
+  count_launch();
+  AB_CUDA_CHECK(cudaGetLastError());
+}
+
+template <typename T>
+static void trsm_rec(int side, int uplo, int trans, int diag, int M, int N, T alpha, const T* A, size_t lda, T* B, size_t ldb,
+                     const int* abort_flag) {
+  using S = ST<T>;
+  const int n = (side == Left) ? M : N;
+  if (n <= TS_NB) { trsm_base<T>(side, uplo, trans, diag, M, N, alpha, A, lda, B, ldb, abort_flag); return; }
+  const int n1 = tri_split(n, TS_NB), n2 = n - n1;
+  const bool eff_lower = (uplo == Lower) != is_tr(trans);
+  const T* A11 = A;
+  const T* A22 = A + (size_t)n1 + (size_t)n1 * lda;
+  const T* Aoff = (uplo == Lower) ? A + n1 : A + (size_t)n1 * lda;
+  const T one = S::one(), none = S::from_real(-1);
+  if (side == Left) {
+    T* B1 = B; T* B2 = B + n1;
+    if (eff_lower) {   // X1 = T11^-1 (alpha B1); B2 <- alpha B2 - T21 X1; X2 = T22^-1 B2
+      trsm_rec<T>(side, uplo, trans, diag, n1, N, alpha, A11, lda, B1, ldb, abort_flag);
+      gemm<T>(trans, NoTrans, n2, N, n1, none, Aoff, lda, B1, ldb, alpha, B2, ldb, abort_flag);
+      trsm_rec<T>(side, uplo, trans, diag, n2, N, one, A22, lda, B2, ldb, abort_flag);
+    } else {           // X2 = T22^-1 (alpha B2); B1 <- alpha B1 - T12 X2; X1 = T11^-1 B1
+      trsm_rec<T>(side, uplo, trans, diag, n2, N, alpha, A22, lda, B2, ldb, abort_flag);
+      gemm<T>(trans, NoTrans, n1, N, n2, none, Aoff, lda, B2, ldb, alpha, B1, ldb, abort_flag);
+      trsm_rec<T>(side, uplo, trans, diag, n1, N, one, A11, lda, B1, ldb, abort_flag);
+    }
+  } else {
+    T* B1 = B; T* B2 = B + (size_t)n1 * ldb;
+    if (eff_lower) {   // X2 = alpha B2 T22^-1; B1 <- alpha B1 - X2 T21; X1 = B1 T11^-1
+      trsm_rec<T>(side, uplo, trans, diag, M, n2, alpha, A22, lda, B2, ldb, abort_flag);
+      gemm<T>(NoTrans, trans, M, n1, n2, none, B2, ldb, Aoff, lda, alpha, B1, ldb, abort_flag);
+      trsm_rec<T>(side, uplo, trans, diag, M, n1, one, A11, lda, B1, ldb, abort_flag);
+    } else {           // X1 = alpha B1 T11^-1; B2 <- alpha B2 - X1 T12; X2 = B2 T22^-1
+      trsm_rec<T>(side, uplo, trans, diag, M, n1, alpha, A11, lda, B1, ldb, abort_flag);
+      gemm<T>(NoTrans, trans, M, n2, n1, none, B1, ldb, Aoff, lda, alpha, B2, ldb, abort_flag);
+      trsm_rec<T>(side, uplo, trans, diag, M, n2, one, A22, lda, B2, ldb, abort_flag);
+    }
+  }
+}
+
+template <typename T>
+void trsm(int side, int uplo, int trans, int diag, int M, int N, T alpha, const T* A, size_t lda, T* B, size_t ldb,
+          const int* abort_flag) {
+  using S = ST<T>;
+  if (M <= 0 || N <= 0) return;
+  if (S::is_zero(alpha)) {  // reference ATL_Xtrsm: alpha==0 -> gescal(0) = zero fill
+    gemm_flags<T>(0, 0, 0, 0, M, N, 0, S::zero(), B, ldb, B, ldb, S::zero(), B, ldb, C_FULL, 0, abort_flag);
+    return;
+  }
+  trsm_rec<T>(side, uplo, trans, diag, M, N, alpha, A, lda, B, ldb, abort_flag);
+}
+
+#define AB_INST(T)                                                                                                     \
+  template void gemm<T>(int, int, int, int, int, T, const T*, size_t, const T*, size_t, T, T*, size_t, const int*);   \
+  template void syrk<T>(int, int, int, int, T, const T*, size_t, T, T*, size_t, const int*);                          \
+  template void trmm<T>(int, int, int, int, int, int, T, const T*, size_t, T*, size_t);                               \
+  template void trsm<T>(int, int, int, int, int, int, T, const T*, size_t, T*, size_t, const int*);
+AB_INST(float) AB_INST(double) AB_INST(float2) AB_INST(double2)
+template void herk<float2>(int, int, int, int, float, const float2*, size_t, float, float2*, size_t, const int*);
+template void herk<double2>(int, int, int, int, double, const double2*, size_t, double, double2*, size_t, const int*);
+
+}  // namespace ab

@@ -1,12 +1,56 @@
-// Per-thread launch stream and launch counter for the product kernels.
-#include "common.cuh"
+// Per-thread launch stream, launch counter and grow-only device workspaces for the product kernels.
+// The reference mallocs and frees its workspace inside every call (atlas-ammm.base:30348+); on the
+// GPU cudaMalloc/cudaFree synchronise the device, so the workspaces are cached per host thread and
+// released by atlb200_free_workspace() / at thread exit.
+#include "ab_api.h"
 #include <atomic>
+
 namespace ab {
+
 static thread_local cudaStream_t g_stream = 0;
 static std::atomic<long long> g_launches{0};
+
 cudaStream_t current_stream() { return g_stream; }
 void set_current_stream(cudaStream_t s) { g_stream = s; }
 void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 long long launch_count() { return g_launches.load(); }
 void reset_launch_count() { g_launches.store(0); }
+
+namespace {
+struct Slots {
+  static constexpr int N = 8;
+  void* ptr[N] = {nullptr};
+  size_t size[N] = {0};
+  int dev[N] = {0};
+  ~Slots() {
+    for (int i = 0; i < N; i++)
+      if (ptr[i]) cudaFree(ptr[i]);   // best effort at thread exit (may run after context teardown)
+  }
+};
+thread_local Slots g_slots;
+}  // namespace
+
+void* workspace(size_t bytes, int slot) {
+  Slots& s = g_slots;
+  int dev = 0;
+  AB_CUDA_CHECK(cudaGetDevice(&dev));
+  if (s.ptr[slot] && s.size[slot] >= bytes && s.dev[slot] == dev) return s.ptr[slot];
+  if (s.ptr[slot]) { AB_CUDA_CHECK(cudaFree(s.ptr[slot])); s.ptr[slot] = nullptr; s.size[slot] = 0; }
+  size_t want = bytes + bytes / 4 + 4096;
+  if (cudaMalloc(&s.ptr[slot], want) != cudaSuccess) {
+    (void)cudaGetLastError();
+    want = bytes;
+    AB_CUDA_CHECK(cudaMalloc(&s.ptr[slot], want));
+  }
+  s.size[slot] = want;
+  s.dev[slot] = dev;
+  return s.ptr[slot];
+}
+
+void free_workspace() {
+  Slots& s = g_slots;
+  for (int i = 0; i < Slots::N; i++)
+    if (s.ptr[i]) { cudaFree(s.ptr[i]); s.ptr[i] = nullptr; s.size[i] = 0; }
+}
+
 }  // namespace ab

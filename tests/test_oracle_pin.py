@@ -56,7 +56,7 @@ def test_gemm(oracle, ref, pre):
         c1, c2 = C0.copy(order="F"), C0.copy(order="F")
         oracle.gemm(pre, ta, tb, M, N, K, al, A, B, be, c1)
         ref.gemm(pre, ta, tb, M, N, K, al, A, B, be, c2)
-        r = _close(pre, c1[:M], c2[:M], max(_nrm1(A), 1) * max(_nrm1(B), 1) * max(_nrm1(C0[:M]), 1), max(M, N, K))
+        r = _close(pre, c1[:M], c2[:M], max(_nrm1(A[:ra]), 1) * max(_nrm1(B[:rb]), 1) * max(_nrm1(C0[:M]), 1), max(M, N, K))
         assert r < 1.0, (pre, M, N, K, ta, tb, al, be, r)
         assert np.array_equal(c1[M:], c2[M:])  # lda gap untouched by both
 
@@ -69,7 +69,7 @@ def test_syrk_herk(oracle, ref, pre):
         C0 = oracle.gegen(pre, N, N, N + 2, N * N + 101 * 2 + 53)
         c1, c2 = C0.copy(order="F"), C0.copy(order="F")
         oracle.syrk(pre, uplo, tr, N, K, al, A, be, c1); ref.syrk(pre, uplo, tr, N, K, al, A, be, c2)
-        r = _close(pre, c1[:N], c2[:N], max(_nrm1(A), 1) ** 2 * max(_nrm1(C0[:N]), 1), max(N, K))
+        r = _close(pre, c1[:N], c2[:N], max(_nrm1(A[:ra]), 1) ** 2 * max(_nrm1(C0[:N]), 1), max(N, K))
         assert r < 1.0, (pre, uplo, tr, N, K, al, be, r)
         other = np.triu_indices(N, 1) if uplo == Lower else np.tril_indices(N, -1)
         assert np.array_equal(c1[:N][other], C0[:N][other])  # untouched triangle
@@ -80,7 +80,7 @@ def test_syrk_herk(oracle, ref, pre):
             C0 = oracle.gegen(pre, N, N, N + 2, N * N + 101 * 2 + 53)
             c1, c2 = C0.copy(order="F"), C0.copy(order="F")
             oracle.herk(pre, uplo, tr, N, K, al, A, be, c1); ref.herk(pre, uplo, tr, N, K, al, A, be, c2)
-            r = _close(pre, c1[:N], c2[:N], max(_nrm1(A), 1) ** 2 * max(_nrm1(C0[:N]), 1), max(N, K))
+            r = _close(pre, c1[:N], c2[:N], max(_nrm1(A[:ra]), 1) ** 2 * max(_nrm1(C0[:N]), 1), max(N, K))
             assert r < 1.0, (pre, uplo, tr, N, K, al, be, r)
             assert np.all(c1[:N][np.arange(N), np.arange(N)].imag == 0)
 

@@ -43,7 +43,7 @@ static int check(int ta, int tb, int M, int N, int K, int pad, double alpha, dou
   AB_CUDA_CHECK(cudaMemcpy(C2, C1, nc * 8, cudaMemcpyDeviceToDevice));
   AB_CUDA_CHECK(cudaMemset(dm, 0, 8));
   bool ok = dgemm_tma(ta, tb, M, N, K, alpha, A, lda, B, ldb, beta, C1, ldc, cmode);
-  GemmP<double> p{M, N, K, A, lda, ta, 0, B, ldb, tb, 0, alpha, beta, C2, ldc, cmode, 0, 0, 0};
+  GemmP<double> p{M, N, K, A, lda, ta, 0, B, ldb, tb, 0, alpha, beta, C2, ldc, cmode, 0, 0, 0, nullptr};
   gemm_generic_launch(p);
   maxdiff_kernel<<<256, 256>>>(C1, C2, ldc, M, N, dm);
   cudaError_t e = cudaDeviceSynchronize();
@@ -83,7 +83,7 @@ static void timeit(int ta, int tb, int N, int reps, bool generic) {
   fill_kernel<<<1024, 256>>>(A, n2, 1); fill_kernel<<<1024, 256>>>(B, n2, 2); fill_kernel<<<1024, 256>>>(C, n2, 3);
   cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
   auto go = [&]() {
-    if (generic) { GemmP<double> p{N, N, N, A, (size_t)N, ta, 0, B, (size_t)N, tb, 0, 1.0, 1.0, C, (size_t)N, 0, 0, 0, 0}; gemm_generic_launch(p); }
+    if (generic) { GemmP<double> p{N, N, N, A, (size_t)N, ta, 0, B, (size_t)N, tb, 0, 1.0, 1.0, C, (size_t)N, 0, 0, 0, 0, nullptr}; gemm_generic_launch(p); }
     else dgemm_tma(ta, tb, N, N, N, 1.0, A, N, B, N, 1.0, C, N, 0);
   };
   go(); AB_CUDA_CHECK(cudaDeviceSynchronize());
