@@ -73,6 +73,7 @@ def _declare(L):
     L.atlb200_launch_count.restype = C.c_longlong
     L.atlb200_last_xerbla.argtypes = [C.c_char_p, I]
     L.atlb200_set_stream.argtypes = [VP]
+    L.atlb200_fp64_dmma_peak_tflops.restype = C.c_double
 
 
 def ptr(x):
@@ -159,6 +160,10 @@ for _p in "sdcz":
     globals()[f"clapack_{_p}potrf"] = _bind(f"clapack_{_p}potrf", clapack_potrf, _p)
     if _CPLX[_p]:
         globals()[f"cblas_{_p}herk"] = _bind(f"cblas_{_p}herk", cblas_herk, _p)
+
+
+def fp64_dmma_peak_tflops():
+    return lib().atlb200_fp64_dmma_peak_tflops()
 
 
 def launch_count():

@@ -24,7 +24,7 @@ def L():
 def declared_symbols():
     txt = open(os.path.join(ROOT, "include", "atlas_b200.h")).read()
     txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
-    return sorted(set(re.findall(r"^\s*(?:void|int|long long)\s+(\w+)\s*\(", txt, flags=re.M)))
+    return sorted(set(re.findall(r"^\s*(?:void|int|long long|double)\s+(\w+)\s*\(", txt, flags=re.M)))
 
 
 def test_header_symbols_exported(L):
