@@ -31,7 +31,37 @@ __global__ void laswp_kernel(int N, T* __restrict__ A, size_t lda, int K1, int K
   if (col >= N) return;
   T* a = A + (size_t)col * lda;
   if (inci >= 0) {
-    for (int i = K1; i < K2; i++) {
+    // Swaps must be applied in order, but a batch of LB consecutive swaps whose 2*LB rows are all
+    // distinct commutes: load all 2*LB elements first (2*LB requests in flight instead of one
+    // dependent round trip per swap), then store them.  The pivot values are the same for every
+    // thread, so the alias test is warp-uniform.
+    constexpr int LB = 16;
+    int i = K1;
+    for (; i + LB <= K2; i += LB) {
+      int ip[LB];
+#pragma unroll
+      for (int b = 0; b < LB; b++) ip[b] = piv[(size_t)(i + b) * inci];
+      bool ok = true;
+#pragma unroll
+      for (int b = 0; b < LB; b++) {
+        if (ip[b] != i + b && ip[b] >= i && ip[b] < i + LB) ok = false;      // target inside the batch's own rows
+#pragma unroll
+        for (int c = 0; c < b; c++)
+          if (ip[b] == ip[c] && ip[b] != i + b) ok = false;                  // two swaps hit the same target
+      }
+      if (ok) {
+        T x[LB], y[LB];
+#pragma unroll
+        for (int b = 0; b < LB; b++) { x[b] = a[i + b]; y[b] = a[ip[b]]; }
+#pragma unroll
+        for (int b = 0; b < LB; b++) { a[i + b] = y[b]; a[ip[b]] = x[b]; }
+      } else {
+        for (int b = 0; b < LB; b++) {
+          if (ip[b] != i + b) { T t = a[i + b]; a[i + b] = a[ip[b]]; a[ip[b]] = t; }
+        }
+      }
+    }
+    for (; i < K2; i++) {
       const int ip = piv[(size_t)i * inci];
       if (ip != i) { T t = a[i]; a[i] = a[ip]; a[ip] = t; }
     }
@@ -48,7 +78,7 @@ __global__ void laswp_kernel(int N, T* __restrict__ A, size_t lda, int K1, int K
 template <typename T>
 void laswp(int N, T* A, size_t lda, int K1, int K2, const int* d_piv, int inci) {
   if (N <= 0 || K2 <= K1) return;
-  const int threads = 128;
+  const int threads = 64;
   laswp_kernel<T><<<(N + threads - 1) / threads, threads, 0, current_stream()>>>(N, A, lda, K1, K2, d_piv, inci);
   count_launch();
   AB_CUDA_CHECK(cudaGetLastError());

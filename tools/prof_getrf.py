@@ -1,0 +1,25 @@
+#!/usr/bin/env python
+"""One warm-up and one timed clapack_dgetrf (device-resident) for kernel-level profiling:
+   ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file out.csv python tools/prof_getrf.py 16384"""
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+import math_atlas_b200 as ab
+n = int(sys.argv[1]) if len(sys.argv) > 1 else 16384
+what = sys.argv[2] if len(sys.argv) > 2 else "getrf"
+dev = torch.device("cuda", 0)
+A0 = torch.rand((n, n), device=dev, dtype=torch.float64) - 0.5
+if what == "potrf":
+    S = torch.zeros_like(A0)
+    ab.cblas_dsyrk(ab.CblasColMajor, ab.CblasLower, ab.CblasNoTrans, n, n, 1.0 / n, A0, n, 0.0, S, n)
+    S += torch.eye(n, device=dev, dtype=torch.float64) * 4.0
+    A0 = S
+W = A0.clone(); piv = torch.zeros(n, dtype=torch.int32, device=dev)
+for it in range(2):
+    W.copy_(A0); torch.cuda.synchronize()
+    ab.reset_launch_count()
+    e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+    e0.record()
+    info = ab.clapack_dgetrf(ab.CblasColMajor, n, n, W, n, piv) if what == "getrf" else ab.clapack_dpotrf(ab.CblasColMajor, ab.CblasLower, n, W, n)
+    e1.record(); torch.cuda.synchronize()
+    print(f"{what} n={n} iter {it}: {e0.elapsed_time(e1):.3f} ms info={info} launches={ab.launch_count()}")
