@@ -128,7 +128,10 @@ struct Operand {
   }
 };
 
-static void sync_stream() { AB_CUDA_CHECK(cudaStreamSynchronize(current_stream())); }
+// async mode (per host thread): device-pointer calls return without draining the stream, so a
+// multi-GPU driver can overlap its collectives with the update kernels (math_atlas_b200/dist.py)
+static thread_local int g_async = 0;
+static void sync_stream() { if (!g_async) AB_CUDA_CHECK(cudaStreamSynchronize(current_stream())); }
 
 // small device scratch for info / pivots when the caller's are on the host
 struct DevInts {
@@ -591,3 +594,17 @@ REAL_API(d, double, "D")
 CPLX_API(c, cfloat, float, "C")
 CPLX_API(z, cdouble, double, "Z")
 }  // extern "C"
+
+// ---- asynchronous device-pointer entry points for the multi-GPU drivers (no reference counterpart):
+// everything (matrix, pivots, info) is in device memory, work is only enqueued on the stream.
+extern "C" {
+void atlb200_set_async(int on) { g_async = on; }
+#define DEV_API(P, T)                                                                                              \
+  void atlb200_##P##getrf_dev(int M, int N, void* A, size_t lda, int* d_ipiv, int* d_info) {                       \
+    getrf<T>(M, N, MP(T, A), lda, d_ipiv, d_info); }                                                                \
+  void atlb200_##P##potrf_dev(int Uplo, int N, void* A, size_t lda, int* d_info) {                                 \
+    potrf<T>(Uplo, N, MP(T, A), lda, d_info); }                                                                     \
+  void atlb200_##P##laswp_dev(int N, void* A, size_t lda, int K1, int K2, const int* d_piv, int inci) {            \
+    laswp<T>(N, MP(T, A), lda, K1, K2, d_piv, inci); }
+DEV_API(s, float) DEV_API(d, double) DEV_API(c, cfloat) DEV_API(z, cdouble)
+}
