@@ -87,7 +87,7 @@ def run_reference(args):
     rank = env_int("RANK", 0)
     if rank != 0:
         return
-    n = args.n
+    n = args.size
     # size the sample from a quick calibration so that steps+warmup stay within a few minutes
     g0, dt0, kind, cores, _ = cpu_dgemm(n, 2, 1, 0)
     per_col = dt0 / 2.0
@@ -168,7 +168,7 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=dev)
     ab.lib()
 
-    n = args.n
+    n = args.size
     assert n % world == 0
     nloc = n // world                      # this rank's slab of columns of B and C
     gen = torch.Generator(device=dev); gen.manual_seed(1234 + rank)
@@ -316,7 +316,7 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--n", type=int, default=16384)
+    ap.add_argument("--size", type=int, default=16384)
     ap.add_argument("--no-getrf", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
