@@ -22,8 +22,11 @@
 #include "dgemm_tma.h"
 #include <cuda.h>
 #include <mutex>
+#include <algorithm>
 
 namespace ab {
+
+int gemm_cta_cap();
 
 namespace {
 
@@ -31,7 +34,7 @@ constexpr int BM = 128, BN = 128, BK = 16, STAGES = 6;
 constexpr int A_TILE_BYTES = BM * BK * 8, B_TILE_BYTES = BN * BK * 8;
 constexpr int STAGE_BYTES = A_TILE_BYTES + B_TILE_BYTES;
 constexpr int CONS_WARPS = 8, THREADS = (CONS_WARPS + 1) * 32;
-constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 2 * STAGES * 8;
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 2 * STAGES * 8 + STAGES * 4 /*tile ring*/;
 constexpr int GROUP_M = 16;  // tile rasterisation group (L2 reuse of the B panel)
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
@@ -80,26 +83,47 @@ __host__ __device__ constexpr uint32_t xm(int j, int hi8) {
   return (jmask(j) << 7) ^ ((((uint32_t)hi8 << 2) ^ jmask(j)) << 4);
 }
 
+// tile index -> tile coordinates (grouped rasterisation: GROUP_M tile rows share their B panel in L2)
+__device__ __forceinline__ void tile_coords(int tile, int tiles_m, int tiles_n, int& m0, int& n0) {
+  const int in_group = GROUP_M * tiles_n;
+  const int first_m = (tile / in_group) * GROUP_M;
+  const int gsz = min(tiles_m - first_m, GROUP_M);
+  m0 = (first_m + (tile % in_group) % gsz) * BM;
+  n0 = ((tile % in_group) / gsz) * BN;
+}
+__device__ __forceinline__ bool tile_skipped(int cmode, int m0, int n0) {
+  return (cmode == C_UPPER && m0 > n0 + BN - 1) || (cmode == C_LOWER && n0 > m0 + BM - 1);
+}
+
+struct SmMask { unsigned long long w[4]; };   // SMs this launch must stay off (look-ahead reservation)
+
+__device__ __forceinline__ unsigned my_smid() { unsigned s; asm volatile("mov.u32 %0, %%smid;" : "=r"(s)); return s; }
+
+// Persistent kernel.  Each resident CTA repeatedly takes a tile - statically (tile = blockIdx.x +
+// n*gridDim.x) or, when `tile_counter` is given, from a global atomic counter - until the list is
+// exhausted.  The producer warp hands the tile index to the consumer warps through the stage ring
+// (tile_ring[s] rides on the full barrier of the tile's first stage; -1 ends the CTA), and the ring
+// with its mbarrier phases runs on across tiles, so the producer prefetches the next tile's first
+// stages while the consumers are still in the epilogue of the current one.
+// CTAs that land on an SM of `reserved` exit at once: during LU/Cholesky look-ahead the update
+// GEMM leaves one GPC's worth of SMs to the panel kernels (a thread-block cluster needs all its
+// SMs free inside one GPC; a grid that is merely capped leaves scattered SMs and the cluster
+// would wait for the GEMM to finish - measured with tools/cluster_coexist_test.cu).
 template <bool A_KMAJOR, bool B_KMAJOR>
 __global__ void __launch_bounds__(THREADS, 1)
 dgemm_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                  double* __restrict__ C, size_t ldc, int M, int N, int K, double alpha, double beta,
-                 int cmode, int tiles_m, int tiles_n, const int* __restrict__ abort_flag) {
+                 int cmode, int tiles_m, int tiles_n, const int* __restrict__ abort_flag,
+                 const SmMask reserved, int* __restrict__ tile_counter) {
   if (abort_flag && *abort_flag) return;  // POTRF stop-at-first-failure (uniform for the whole grid)
-  // ---- tile coordinates (grouped rasterisation) ----
-  const int pid = blockIdx.x;
-  const int in_group = GROUP_M * tiles_n;
-  const int first_m = (pid / in_group) * GROUP_M;
-  const int gsz = min(tiles_m - first_m, GROUP_M);
-  const int tile_m = first_m + (pid % in_group) % gsz;
-  const int tile_n = (pid % in_group) / gsz;
-  const int m0 = tile_m * BM, n0 = tile_n * BN;
-  if (cmode == C_UPPER && m0 > n0 + BN - 1) return;
-  if (cmode == C_LOWER && n0 > m0 + BM - 1) return;
-
+  {
+    const unsigned sm = my_smid();
+    if ((reserved.w[(sm >> 6) & 3] >> (sm & 63)) & 1ull) return;
+  }
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t bar_base = smem_base + STAGES * STAGE_BYTES;  // full[s] at +8s, empty[s] at +8(STAGES+s)
+  const uint32_t ring_base = bar_base + 2 * STAGES * 8;        // int tile_ring[STAGES]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
@@ -112,22 +136,40 @@ dgemm_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   __syncthreads();
 
   const int KT = (K + BK - 1) / BK;
+  const int ntiles = tiles_m * tiles_n;
 
   if (warp == CONS_WARPS) {
     // ===================== TMA producer warp =====================
-    for (int kt = 0; kt < KT; kt++) {
-      const int s = kt % STAGES;
-      const uint32_t ph = (kt / STAGES) & 1;
-      mbar_wait(bar_base + 8 * (STAGES + s), ph ^ 1);
-      const uint32_t full = bar_base + 8 * s;
-      const uint32_t sa = smem_base + s * STAGE_BYTES, sb = sa + A_TILE_BYTES;
-      const int k0 = kt * BK;
-      if (lane == 0) mbar_expect_tx(full, STAGE_BYTES);
-      __syncwarp();
-      if (A_KMAJOR) { if (lane == 0) tma_load_2d(sa, &tmA, k0, m0, full); }
-      else          { if (lane < 8) tma_load_2d(sa + lane * 2048, &tmA, m0 + 16 * lane, k0, full); }
-      if (B_KMAJOR) { if (lane == 16) tma_load_2d(sb, &tmB, k0, n0, full); }
-      else          { if (lane >= 16 && lane < 24) tma_load_2d(sb + (lane - 16) * 2048, &tmB, n0 + 16 * (lane - 16), k0, full); }
+    uint32_t it = 0;   // running stage counter across tiles
+    int next_static = blockIdx.x;
+    for (;;) {
+      int tile;
+      if (tile_counter) { tile = (lane == 0) ? atomicAdd(tile_counter, 1) : 0; tile = __shfl_sync(0xffffffffu, tile, 0); }
+      else { tile = next_static; next_static += gridDim.x; }
+      const bool done = tile >= ntiles;
+      int m0 = 0, n0 = 0;
+      if (!done) {
+        tile_coords(tile, tiles_m, tiles_n, m0, n0);
+        if (tile_skipped(cmode, m0, n0)) continue;
+      }
+      const int nk = done ? 1 : KT;
+      for (int kt = 0; kt < nk; kt++, it++) {
+        const uint32_t s = it % STAGES;
+        const uint32_t ph = (it / STAGES) & 1;
+        mbar_wait(bar_base + 8 * (STAGES + s), ph ^ 1);
+        const uint32_t full = bar_base + 8 * s;
+        if (kt == 0 && lane == 0) asm volatile("st.shared.s32 [%0], %1;" ::"r"(ring_base + 4 * s), "r"(done ? -1 : tile) : "memory");
+        if (done) { if (lane == 0) mbar_arrive(full); break; }
+        const uint32_t sa = smem_base + s * STAGE_BYTES, sb = sa + A_TILE_BYTES;
+        const int k0 = kt * BK;
+        if (lane == 0) mbar_expect_tx(full, STAGE_BYTES);
+        __syncwarp();
+        if (A_KMAJOR) { if (lane == 0) tma_load_2d(sa, &tmA, k0, m0, full); }
+        else          { if (lane < 8) tma_load_2d(sa + lane * 2048, &tmA, m0 + 16 * lane, k0, full); }
+        if (B_KMAJOR) { if (lane == 16) tma_load_2d(sb, &tmB, k0, n0, full); }
+        else          { if (lane >= 16 && lane < 24) tma_load_2d(sb + (lane - 16) * 2048, &tmB, n0 + 16 * (lane - 16), k0, full); }
+      }
+      if (done) break;
     }
     return;
   }
@@ -141,61 +183,75 @@ dgemm_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   const uint32_t LM = base_t * 128u + (((((uint32_t)g >> 1) ^ (base_t & 7u)) & 7u) << 4) + (((uint32_t)g & 1u) << 3);
   const uint32_t a_lane = A_KMAJOR ? (uint32_t)(wm * 64) * 128u + LK : (uint32_t)(wm * 4) * 2048u + LM;
   const uint32_t b_lane = B_KMAJOR ? (uint32_t)(wn * 32) * 128u + LK : (uint32_t)(wn * 2) * 2048u + LM;
-
-  double acc[8][4][2];
-#pragma unroll
-  for (int i = 0; i < 8; i++)
-#pragma unroll
-    for (int j = 0; j < 4; j++) { acc[i][j][0] = 0.; acc[i][j][1] = 0.; }
-
-  for (int kt = 0; kt < KT; kt++) {
-    const int s = kt % STAGES;
-    const uint32_t ph = (kt / STAGES) & 1;
-    mbar_wait(bar_base + 8 * s, ph);
-    const uint32_t sa = smem_base + s * STAGE_BYTES, sb = sa + A_TILE_BYTES;
-#pragma unroll
-    for (int j = 0; j < 4; j++) {
-      double a[8], b[4];
-#pragma unroll
-      for (int mi = 0; mi < 8; mi++) {
-        // K-major: rows advance 8*128 B per mi; MN-major: 16-row group = 2048 B, (mi&1) picks the half
-        const uint32_t off = A_KMAJOR ? ((a_lane + mi * 1024u) ^ xk(j))
-                                      : (a_lane + (mi >> 1) * 2048u) ^ xm(j, mi & 1);
-        a[mi] = lds_f64(sa + off);
-      }
-#pragma unroll
-      for (int ni = 0; ni < 4; ni++) {
-        const uint32_t off = B_KMAJOR ? ((b_lane + ni * 1024u) ^ xk(j))
-                                      : (b_lane + (ni >> 1) * 2048u) ^ xm(j, ni & 1);
-        b[ni] = lds_f64(sb + off);
-      }
-#pragma unroll
-      for (int mi = 0; mi < 8; mi++)
-#pragma unroll
-        for (int ni = 0; ni < 4; ni++) dmma884(acc[mi][ni][0], acc[mi][ni][1], a[mi], b[ni]);
-    }
-    __syncwarp();
-    if (lane == 0) mbar_arrive(bar_base + 8 * (STAGES + s));
-  }
-
-  // ---- epilogue: C = alpha*acc + beta*C (ablk2cmat, atlas-ammm.base:550), triangle mask for SYRK ----
   const bool beta0 = (beta == 0.);
+
+  uint32_t it = 0;
+  for (;;) {
+    // the first stage of a tile carries the tile index (or the end marker)
+    {
+      const uint32_t s = it % STAGES;
+      mbar_wait(bar_base + 8 * s, (it / STAGES) & 1);
+    }
+    int tile;
+    asm volatile("ld.shared.s32 %0, [%1];" : "=r"(tile) : "r"(ring_base + 4 * (it % STAGES)) : "memory");
+    if (tile < 0) break;
+    int m0, n0;
+    tile_coords(tile, tiles_m, tiles_n, m0, n0);
+
+    double acc[8][4][2];
 #pragma unroll
-  for (int ni = 0; ni < 4; ni++) {
+    for (int i = 0; i < 8; i++)
 #pragma unroll
-    for (int e = 0; e < 2; e++) {
-      const int n = n0 + wn * 32 + ni * 8 + 2 * t + e;
-      if (n >= N) continue;
-      double* cc = C + (size_t)n * ldc;
+      for (int j = 0; j < 4; j++) { acc[i][j][0] = 0.; acc[i][j][1] = 0.; }
+
+    for (int kt = 0; kt < KT; kt++, it++) {
+      const uint32_t s = it % STAGES;
+      const uint32_t ph = (it / STAGES) & 1;
+      if (kt > 0) mbar_wait(bar_base + 8 * s, ph);
+      const uint32_t sa = smem_base + s * STAGE_BYTES, sb = sa + A_TILE_BYTES;
 #pragma unroll
-      for (int mi = 0; mi < 8; mi++) {
-        const int m = m0 + wm * 64 + mi * 8 + g;
-        if (m >= M) continue;
-        if (cmode == C_UPPER && m > n) continue;
-        if (cmode == C_LOWER && m < n) continue;
-        double r = alpha * acc[mi][ni][e];
-        if (!beta0) r += beta * cc[m];
-        cc[m] = r;
+      for (int j = 0; j < 4; j++) {
+        double a[8], b[4];
+#pragma unroll
+        for (int mi = 0; mi < 8; mi++) {
+          // K-major: rows advance 8*128 B per mi; MN-major: 16-row group = 2048 B, (mi&1) picks the half
+          const uint32_t off = A_KMAJOR ? ((a_lane + mi * 1024u) ^ xk(j))
+                                        : (a_lane + (mi >> 1) * 2048u) ^ xm(j, mi & 1);
+          a[mi] = lds_f64(sa + off);
+        }
+#pragma unroll
+        for (int ni = 0; ni < 4; ni++) {
+          const uint32_t off = B_KMAJOR ? ((b_lane + ni * 1024u) ^ xk(j))
+                                        : (b_lane + (ni >> 1) * 2048u) ^ xm(j, ni & 1);
+          b[ni] = lds_f64(sb + off);
+        }
+#pragma unroll
+        for (int mi = 0; mi < 8; mi++)
+#pragma unroll
+          for (int ni = 0; ni < 4; ni++) dmma884(acc[mi][ni][0], acc[mi][ni][1], a[mi], b[ni]);
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_base + 8 * (STAGES + s));
+    }
+
+    // ---- epilogue: C = alpha*acc + beta*C (ablk2cmat, atlas-ammm.base:550), triangle mask for SYRK ----
+#pragma unroll
+    for (int ni = 0; ni < 4; ni++) {
+#pragma unroll
+      for (int e = 0; e < 2; e++) {
+        const int n = n0 + wn * 32 + ni * 8 + 2 * t + e;
+        if (n >= N) continue;
+        double* cc = C + (size_t)n * ldc;
+#pragma unroll
+        for (int mi = 0; mi < 8; mi++) {
+          const int m = m0 + wm * 64 + mi * 8 + g;
+          if (m >= M) continue;
+          if (cmode == C_UPPER && m > n) continue;
+          if (cmode == C_LOWER && m < n) continue;
+          double r = alpha * acc[mi][ni][e];
+          if (!beta0) r += beta * cc[m];
+          cc[m] = r;
+        }
       }
     }
   }
@@ -230,6 +286,13 @@ bool make_map(CUtensorMap* tm, const double* ptr, size_t rows, size_t cols, size
   return r == CUDA_SUCCESS;
 }
 
+// look-ahead reservation state of the calling thread (set by set_gemm_reserved)
+thread_local SmMask g_reserved = {{0, 0, 0, 0}};
+thread_local bool g_reserved_on = false;
+thread_local int* g_counters = nullptr;     // ring of device tile counters
+thread_local int g_counter_next = 0;
+constexpr int NCOUNTERS = 256;
+
 template <bool AK, bool BK_>
 void launch(const CUtensorMap& ta, const CUtensorMap& tb, double* C, size_t ldc, int M, int N, int K, double alpha,
             double beta, int cmode, const int* abort_flag) {
@@ -239,13 +302,38 @@ void launch(const CUtensorMap& ta, const CUtensorMap& tb, double* C, size_t ldc,
     attr_set = true;
   }
   const int tiles_m = (M + BM - 1) / BM, tiles_n = (N + BN - 1) / BN;
-  dgemm_tma_kernel<AK, BK_><<<tiles_m * tiles_n, THREADS, SMEM_BYTES, current_stream()>>>(
-      ta, tb, C, ldc, M, N, K, alpha, beta, cmode, tiles_m, tiles_n, abort_flag);
+  int grid = std::min(tiles_m * tiles_n, gemm_cta_cap());
+  SmMask mask = {{0, 0, 0, 0}};
+  int* counter = nullptr;
+  if (g_reserved_on && tiles_m * tiles_n > 16) {
+    // one CTA per SM, the ones on reserved SMs leave, the rest share the tiles through a counter
+    mask = g_reserved;
+    grid = gemm_cta_cap();
+    if (!g_counters) AB_CUDA_CHECK(cudaMalloc(&g_counters, NCOUNTERS * sizeof(int)));
+    counter = g_counters + (g_counter_next++ % NCOUNTERS);
+    AB_CUDA_CHECK(cudaMemsetAsync(counter, 0, sizeof(int), current_stream()));
+  }
+  dgemm_tma_kernel<AK, BK_><<<grid, THREADS, SMEM_BYTES, current_stream()>>>(
+      ta, tb, C, ldc, M, N, K, alpha, beta, cmode, tiles_m, tiles_n, abort_flag, mask, counter);
   count_launch();
   AB_CUDA_CHECK(cudaGetLastError());
 }
 
 }  // namespace
+
+// persistent-grid size: all SMs unless the caller reserved some (set_gemm_cta_cap)
+static thread_local int g_cta_cap = 0;
+int gemm_cta_cap() {
+  if (g_cta_cap > 0) return g_cta_cap;
+  static int sms = 0;
+  if (!sms) { int dev; AB_CUDA_CHECK(cudaGetDevice(&dev)); AB_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev)); }
+  return sms;
+}
+void set_gemm_cta_cap(int cap) { g_cta_cap = cap; }
+void set_gemm_reserved(const unsigned long long* mask4) {
+  if (mask4) { for (int i = 0; i < 4; i++) g_reserved.w[i] = mask4[i]; g_reserved_on = true; }
+  else g_reserved_on = false;
+}
 
 bool dgemm_tma_eligible(int M, int N, int K, const double* A, size_t lda, const double* B, size_t ldb) {
   // TMA needs 16-byte aligned base and row pitch (global stride multiple of 16 B => even ld).

@@ -19,53 +19,59 @@
 //   potf2_kernel        replaces ATL_potrf2 / potrfL_{2,3,4} (:737-905): one CTA, block in shared memory.
 //   laswp_kernel        replaces ATL_laswp (:1053): one thread per column, pivots applied in order.
 #include "ab_api.h"
+#include "lu_panel_cluster.cuh"
+#include "dgemm_tma.h"
 #include <cfloat>
 #include <type_traits>
 
 namespace ab {
 
 // ------------------------------------------------------------------------------------- laswp
+// One thread per column.  Swaps must be applied in order, but a batch of 32 consecutive swaps whose
+// 64 rows are pairwise distinct commutes: then all 64 elements are loaded first (64 requests in
+// flight instead of one dependent round trip per swap) and stored afterwards.  Lane b of the warp
+// holds pivot i+b (one coalesced load, prefetched one batch ahead); the alias test is a
+// __match_any / __any over the warp, and every thread gets pivot b by shuffle.
 template <typename T>
-__global__ void laswp_kernel(int N, T* __restrict__ A, size_t lda, int K1, int K2, const int* __restrict__ piv, int inci) {
+__global__ void __launch_bounds__(64) laswp_kernel(int N, T* __restrict__ A, size_t lda, int K1, int K2,
+                                                    const int* __restrict__ piv, int inci) {
   const int col = blockIdx.x * blockDim.x + threadIdx.x;
-  if (col >= N) return;
-  T* a = A + (size_t)col * lda;
+  const bool active = col < N;
+  const int lane = threadIdx.x & 31;
+  T* a = A + (size_t)(active ? col : 0) * lda;
   if (inci >= 0) {
-    // Swaps must be applied in order, but a batch of LB consecutive swaps whose 2*LB rows are all
-    // distinct commutes: load all 2*LB elements first (2*LB requests in flight instead of one
-    // dependent round trip per swap), then store them.  The pivot values are the same for every
-    // thread, so the alias test is warp-uniform.
-    constexpr int LB = 16;
-    int i = K1;
-    for (; i + LB <= K2; i += LB) {
-      int ip[LB];
-#pragma unroll
-      for (int b = 0; b < LB; b++) ip[b] = piv[(size_t)(i + b) * inci];
-      bool ok = true;
-#pragma unroll
-      for (int b = 0; b < LB; b++) {
-        if (ip[b] != i + b && ip[b] >= i && ip[b] < i + LB) ok = false;      // target inside the batch's own rows
-#pragma unroll
-        for (int c = 0; c < b; c++)
-          if (ip[b] == ip[c] && ip[b] != i + b) ok = false;                  // two swaps hit the same target
-      }
+    constexpr int LB = 32;
+    int nextp = (K1 + lane < K2) ? piv[(size_t)(K1 + lane) * inci] : -1;
+    for (int i = K1; i < K2; i += LB) {
+      const int cnt = min(LB, K2 - i);           // the last batch may be partial: extra lanes are no-ops
+      const int myp = nextp;
+      nextp = (i + LB + lane < K2) ? piv[(size_t)(i + LB + lane) * inci] : -1;
+      const bool noop = (lane >= cnt) || (myp == i + lane);
+      // aliasing: a target inside the batch's own row range, or two swaps with the same target
+      const bool inrange = !noop && myp >= i && myp < i + cnt;
+      const unsigned same = __match_any_sync(0xffffffffu, noop ? -1 - lane : myp);
+      const bool dup = !noop && (__popc(same) > 1);
+      const bool ok = !__any_sync(0xffffffffu, inrange || dup);
       if (ok) {
         T x[LB], y[LB];
 #pragma unroll
-        for (int b = 0; b < LB; b++) { x[b] = a[i + b]; y[b] = a[ip[b]]; }
-#pragma unroll
-        for (int b = 0; b < LB; b++) { a[i + b] = y[b]; a[ip[b]] = x[b]; }
-      } else {
         for (int b = 0; b < LB; b++) {
-          if (ip[b] != i + b) { T t = a[i + b]; a[i + b] = a[ip[b]]; a[ip[b]] = t; }
+          const int ipb = __shfl_sync(0xffffffffu, myp, b);
+          if (active && b < cnt) { x[b] = a[i + b]; y[b] = a[ipb]; }
+        }
+#pragma unroll
+        for (int b = 0; b < LB; b++) {
+          const int ipb = __shfl_sync(0xffffffffu, myp, b);
+          if (active && b < cnt) { a[i + b] = y[b]; a[ipb] = x[b]; }
+        }
+      } else {
+        for (int b = 0; b < cnt; b++) {
+          const int ipb = __shfl_sync(0xffffffffu, myp, b);
+          if (active && ipb != i + b) { T t = a[i + b]; a[i + b] = a[ipb]; a[ipb] = t; }
         }
       }
     }
-    for (; i < K2; i++) {
-      const int ip = piv[(size_t)i * inci];
-      if (ip != i) { T t = a[i]; a[i] = a[ip]; a[ip] = t; }
-    }
-  } else {
+  } else if (active) {
     // reference: piv -= (K2-1)*inci ; i runs K2-1 .. K1 reading consecutive entries
     const int* p = piv - (ptrdiff_t)(K2 - 1) * inci;
     for (int i = K2 - 1; i >= K1; i--, p += inci) {
@@ -135,7 +141,7 @@ __device__ __forceinline__ void grid_barrier(unsigned* counter, unsigned target)
 template <typename T, int W, int RPT>
 __global__ void __launch_bounds__(PNL_THREADS)
 getf2_panel_kernel(int M, int w, T* __restrict__ A, size_t lda, int* __restrict__ ipiv, int* __restrict__ info,
-                   unsigned* __restrict__ counter, typename ST<T>::real* __restrict__ cval, int* __restrict__ crow,
+                   int piv_off, int info_off, unsigned* __restrict__ counter, typename ST<T>::real* __restrict__ cval, int* __restrict__ crow,
                    T* __restrict__ crows, T* __restrict__ jrow) {
   using S = ST<T>;
   using R = typename S::real;
@@ -240,8 +246,8 @@ getf2_panel_kernel(int M, int w, T* __restrict__ A, size_t lda, int* __restrict_
       const T piv = s_prow[j];
       const bool nonzero = !S::is_zero(piv);
       if (b == 0 && tid == 0) {
-        ipiv[j] = p;
-        if (!nonzero && *info == 0) *info = j + 1;
+        ipiv[j] = p + piv_off;
+        if (!nonzero && *info == 0) *info = info_off + j + 1;
       }
       // ---- 6. row exchange (only when the pivot is non-zero, like LU1), 7. scale + rank-1 update
       T rcp = S::zero();
@@ -302,7 +308,7 @@ static long panel_capacity() {   // rows that fit co-resident for this variant
 }
 
 template <typename T, int W, int RPT>
-static void panel_launch(int M, int w, T* A, size_t lda, int* d_ipiv, int* d_info) {
+static void panel_launch(int M, int w, T* A, size_t lda, int* d_ipiv, int* d_info, int piv_off, int info_off) {
   using R = typename ST<T>::real;
   const int nb = (M + PNL_THREADS * RPT - 1) / (PNL_THREADS * RPT);
   // workspace: counter | cval | crow | crows | jrow
@@ -319,7 +325,7 @@ static void panel_launch(int M, int w, T* A, size_t lda, int* d_ipiv, int* d_inf
   int* crow = reinterpret_cast<int*>(ws + o_crow);
   T* crows = reinterpret_cast<T*>(ws + o_crows);
   T* jrow = reinterpret_cast<T*>(ws + o_crows + ((steps * nb * W * sizeof(T) + 255) / 256) * 256);
-  void* args[] = {&M, &w, &A, &lda, &d_ipiv, &d_info, &counter, &cval, &crow, &crows, &jrow};
+  void* args[] = {&M, &w, &A, &lda, &d_ipiv, &d_info, &piv_off, &info_off, &counter, &cval, &crow, &crows, &jrow};
   AB_CUDA_CHECK(cudaLaunchCooperativeKernel((void*)getf2_panel_kernel<T, W, RPT>, dim3(nb), dim3(PNL_THREADS), args, 0,
                                             current_stream()));
   count_launch();
@@ -338,21 +344,51 @@ static int panel_width_for(int M) {
 
 // factor an M x w panel, w <= leaf_w (the width panel_width_for() chose for the whole factorisation)
 template <typename T>
-static void getf2_panel(int M, int w, int leaf_w, T* A, size_t lda, int* d_ipiv, int* d_info) {
+static void getf2_panel(int M, int w, int leaf_w, T* A, size_t lda, int* d_ipiv, int* d_info, int piv_off, int info_off) {
   constexpr int W = PanelW<T>::W;
-  if (leaf_w == W) panel_launch<T, W, 1>(M, w, A, lda, d_ipiv, d_info);
-  else if (leaf_w == W / 2) panel_launch<T, W / 2, 2>(M, w, A, lda, d_ipiv, d_info);
-  else panel_launch<T, W / 4, 4>(M, w, A, lda, d_ipiv, d_info);
+  if (leaf_w == W) panel_launch<T, W, 1>(M, w, A, lda, d_ipiv, d_info, piv_off, info_off);
+  else if (leaf_w == W / 2) panel_launch<T, W / 2, 2>(M, w, A, lda, d_ipiv, d_info, piv_off, info_off);
+  else panel_launch<T, W / 4, 4>(M, w, A, lda, d_ipiv, d_info, piv_off, info_off);
+}
+
+// Leaf selection.  A panel of M rows is factored by the cluster kernel when one cluster can hold it
+// (16 CTAs x 512 threads x RPT rows; narrower leaves hold more rows per thread), else by the
+// global-barrier kernel.  The width is chosen per recursion node, so leaves widen as M shrinks.
+template <typename T>
+static int leaf_width_for(int M, bool* use_cluster) {
+  constexpr int E = PanelW<T>::W;
+  *use_cluster = true;
+  if (M <= cluster_capacity<T, E, 1>()) return E;
+  if (M <= cluster_capacity<T, E / 2, 2>()) return E / 2;
+  // (an E/4-wide cluster leaf would hold 4x the rows, but measured slower than the global-barrier
+  //  kernel at full width: too many tiny leaves and level-above launches)
+  *use_cluster = false;
+  return panel_width_for<T>(M);
 }
 
 template <typename T>
-static void getrf_rec(int M, int N, T* A, size_t lda, int* d_ipiv, int* d_info, int* d_sub, int leaf_w) {
+static void getf2_leaf(int M, int w, int lw, bool use_cluster, T* A, size_t lda, int* d_ipiv, int* d_info, int piv_off, int info_off) {
+  constexpr int E = PanelW<T>::W;
+  if (!use_cluster) { getf2_panel<T>(M, w, lw, A, lda, d_ipiv, d_info, piv_off, info_off); return; }
+  if (lw == E) cluster_launch<T, E, 1>(M, w, A, lda, d_ipiv, d_info, piv_off, info_off);
+  else if (lw == E / 2) cluster_launch<T, E / 2, 2>(M, w, A, lda, d_ipiv, d_info, piv_off, info_off);
+  else cluster_launch<T, E / 4, 4>(M, w, A, lda, d_ipiv, d_info, piv_off, info_off);
+}
+
+// Factor the M x N block whose top-left corner is (r0, r0) of the matrix A0.  Pivot indices and
+// info are kept ABSOLUTE (relative to row/column 0 of A0): the leaves write them that way and the
+// row interchanges address whole columns of A0, so the reference's "ipiv[i] += Nleft" pass and its
+// info bookkeeping (atlas-lp.base:1556-1560) need no kernels of their own.
+template <typename T>
+static void getrf_rec(T* A0, size_t lda, int r0, int M, int N, int* d_ipiv, int* d_info) {
   using S = ST<T>;
   const int MN = min(M, N);
   if (MN <= 0) return;
+  T* A = A0 + (size_t)r0 + (size_t)r0 * lda;
+  bool use_cluster;
+  const int leaf_w = leaf_width_for<T>(M, &use_cluster);
   if (N <= leaf_w) {
-    // leaf: d_sub is a scratch info for the panel, merged by the caller
-    getf2_panel<T>(M, N, leaf_w, A, lda, d_ipiv, d_info);
+    getf2_leaf<T>(M, N, leaf_w, use_cluster, A, lda, d_ipiv + r0, d_info, r0, r0);
     return;
   }
   // Nleft = MN/2 rounded down to a multiple of the leaf width (the reference rounds to its tuned
@@ -363,22 +399,88 @@ static void getrf_rec(int M, int N, T* A, size_t lda, int* d_ipiv, int* d_info, 
   const int Nright = N - Nleft;
   T* Ac = A + (size_t)Nleft * lda;
   T* An = Ac + Nleft;
-  getrf_rec<T>(M, Nleft, A, lda, d_ipiv, d_info, d_sub, leaf_w);
-  laswp<T>(Nright, Ac, lda, 0, Nleft, d_ipiv, 1);
+  getrf_rec<T>(A0, lda, r0, M, Nleft, d_ipiv, d_info);
+  laswp<T>(Nright, A0 + (size_t)(r0 + Nleft) * lda, lda, r0, r0 + Nleft, d_ipiv, 1);
   trsm<T>(Left, Lower, NoTrans, Unit, Nleft, Nright, S::one(), A, lda, Ac, lda);
   gemm<T>(NoTrans, NoTrans, M - Nleft, Nright, Nleft, S::from_real(-1), A + Nleft, lda, Ac, lda, S::one(), An, lda);
   if (M - Nleft > 0) {
-    AB_CUDA_CHECK(cudaMemsetAsync(d_sub, 0, sizeof(int), current_stream()));
-    int* d_sub2 = d_sub + 1;   // scratch chain: one int per recursion depth
-    getrf_rec<T>(M - Nleft, Nright, An, lda, d_ipiv + Nleft, d_sub, d_sub2, leaf_w);
-    const int nr = MN - Nleft;
-    if (nr > 0) {
-      ipiv_add_kernel<<<(nr + 255) / 256, 256, 0, current_stream()>>>(d_ipiv + Nleft, nr, Nleft);
-      count_launch();
+    getrf_rec<T>(A0, lda, r0 + Nleft, M - Nleft, Nright, d_ipiv, d_info);
+    laswp<T>(Nleft, A0 + (size_t)r0 * lda, lda, r0 + Nleft, r0 + MN, d_ipiv, 1);
+  }
+}
+
+// ---- look-ahead: a second stream for the panel chain ------------------------------------------
+// The recursion above is a single chain of kernels; at N=16384 two thirds of its time are the
+// latency-bound pieces (leaves, small TRSM/GEMM/laswp), during which the tensor pipe idles.
+// For large matrices the top level is therefore unrolled into block steps of NB columns
+// (right-looking, as the reference's ATL_tgetrf_bcAmm does, Students/fact-amm.base:73): panel k+1
+// is factored (recursively, on the side stream) as soon as its own columns have received update k,
+// while the main stream applies update k to the rest of the trailing matrix.  Pivoting is
+// unchanged (the same column-by-column search on the same updated values).
+namespace {
+struct SideStream {
+  cudaStream_t st = nullptr;
+  cudaEvent_t cols[2] = {nullptr, nullptr}, panel[2] = {nullptr, nullptr};
+  int dev = -1;
+  void ensure() {
+    int d; AB_CUDA_CHECK(cudaGetDevice(&d));
+    if (st && d == dev) return;
+    dev = d;
+    AB_CUDA_CHECK(cudaStreamCreateWithPriority(&st, cudaStreamNonBlocking, -1));   // panel work first
+    for (int i = 0; i < 2; i++) {
+      AB_CUDA_CHECK(cudaEventCreateWithFlags(&cols[i], cudaEventDisableTiming));
+      AB_CUDA_CHECK(cudaEventCreateWithFlags(&panel[i], cudaEventDisableTiming));
     }
-    info_merge_kernel<<<1, 1, 0, current_stream()>>>(d_info, d_sub, Nleft);
-    count_launch();
-    laswp<T>(Nleft, A, lda, Nleft, MN, d_ipiv, 1);
+  }
+};
+thread_local SideStream g_side;
+int env_int(const char* name, int dflt) { const char* v = getenv(name); return v ? atoi(v) : dflt; }
+}  // namespace
+
+template <typename T>
+static void lu_apply_panel(T* A, size_t lda, int M, int k0, int w, int c0, int nc, const int* d_ipiv) {
+  // columns [c0, c0+nc) receive panel [k0, k0+w): interchanges, U block row, Schur complement
+  using S = ST<T>;
+  if (nc <= 0) return;
+  laswp<T>(nc, A + (size_t)c0 * lda, lda, k0, k0 + w, d_ipiv, 1);
+  trsm<T>(Left, Lower, NoTrans, Unit, w, nc, S::one(), A + (size_t)k0 + (size_t)k0 * lda, lda, A + (size_t)k0 + (size_t)c0 * lda, lda);
+  if (M - k0 - w > 0)
+    gemm<T>(NoTrans, NoTrans, M - k0 - w, nc, w, S::from_real(-1), A + (size_t)(k0 + w) + (size_t)k0 * lda, lda,
+            A + (size_t)k0 + (size_t)c0 * lda, lda, S::one(), A + (size_t)(k0 + w) + (size_t)c0 * lda, lda);
+}
+
+template <typename T>
+static void getrf_lookahead(int M, int N, T* A, size_t lda, int* d_ipiv, int* d_info, int NB) {
+  const int MN = min(M, N);
+  SideStream& ss = g_side;
+  ss.ensure();
+  cudaStream_t U = current_stream(), P = ss.st;
+  // SMs of one GPC are kept free of update-GEMM CTAs while a panel is being factored beside it
+  const unsigned long long* reserved = env_int("ATLB200_LU_RESERVE", 1) ? cluster_reserved_mask() : nullptr;
+
+  getrf_rec<T>(A, lda, 0, M, min(NB, N), d_ipiv, d_info);           // panel 0 on the main stream
+  for (int k0 = 0, k = 0; k0 < MN; k0 += NB, k++) {
+    const int w = min(NB, MN - k0);
+    const int c1 = k0 + w;                       // first column right of the panel
+    const int nright = N - c1;
+    const bool more = (c1 < MN);                 // is there a next panel to factor?
+    if (nright > 0) {
+      const int w1 = more ? min(NB, N - c1) : 0;
+      if (more) {
+        lu_apply_panel<T>(A, lda, M, k0, w, c1, w1, d_ipiv);          // next panel's columns first
+        AB_CUDA_CHECK(cudaEventRecord(ss.cols[k & 1], U));
+        AB_CUDA_CHECK(cudaStreamWaitEvent(P, ss.cols[k & 1], 0));
+        set_current_stream(P);
+        getrf_rec<T>(A, lda, c1, M - c1, w1, d_ipiv, d_info);         // panel k+1 beside the update
+        AB_CUDA_CHECK(cudaEventRecord(ss.panel[k & 1], P));
+        set_current_stream(U);
+        set_gemm_reserved(reserved);                                   // leave a GPC to the panel kernels
+      }
+      lu_apply_panel<T>(A, lda, M, k0, w, c1 + w1, nright - w1, d_ipiv);
+      set_gemm_reserved(nullptr);
+    }
+    if (k0 > 0) laswp<T>(k0, A, lda, k0, k0 + w, d_ipiv, 1);           // interchanges left of the panel
+    if (more && nright > 0) AB_CUDA_CHECK(cudaStreamWaitEvent(U, ss.panel[k & 1], 0));
   }
 }
 
@@ -386,8 +488,9 @@ template <typename T>
 void getrf(int M, int N, T* A, size_t lda, int* d_ipiv, int* d_info) {
   AB_CUDA_CHECK(cudaMemsetAsync(d_info, 0, sizeof(int), current_stream()));
   if (M <= 0 || N <= 0) return;
-  int* d_sub = static_cast<int*>(workspace(64 * sizeof(int), 2));
-  getrf_rec<T>(M, N, A, lda, d_ipiv, d_info, d_sub, panel_width_for<T>(M));
+  const int NB = env_int("ATLB200_LU_NB", 256);
+  if (env_int("ATLB200_LU_LOOKAHEAD", 1) && NB > 0 && min(M, N) >= 4 * NB) getrf_lookahead<T>(M, N, A, lda, d_ipiv, d_info, NB);
+  else getrf_rec<T>(A, lda, 0, M, N, d_ipiv, d_info);
 }
 
 // ------------------------------------------------------------------------------------- Cholesky leaf

@@ -149,8 +149,11 @@ void trmm(int side, int uplo, int trans, int diag, int M, int N, T alpha, const 
 }
 
 // ------------------------------------------------------------------------------------- TRSM
-constexpr int TS_NB = 32;     // base triangle size
-constexpr int TS_VEC = 64;    // right-hand sides (threads) per CTA
+// base triangle size (the recursion above it is GEMM)
+template <typename T> struct TsNB { static constexpr int V = 64; };
+template <> struct TsNB<double2> { static constexpr int V = 32; };
+constexpr int TS_VEC = 64;     // right-hand sides per CTA
+constexpr int TS_Q = 4;        // threads per right-hand side (rows interleaved mod 4)
 
 template <typename T> __device__ __forceinline__ T s_recip(T d) { return ST<T>::one() / d; }
 template <> __device__ __forceinline__ float2 s_recip<float2>(float2 a) {  // Smith, like ATL_Xcplxinvert
@@ -163,59 +166,92 @@ template <> __device__ __forceinline__ double2 s_recip<double2>(double2 a) {
   if (fabs(a.x) >= fabs(a.y)) { t = a.y / a.x; d = a.x + a.y * t; return make_double2(1. / d, -t / d); }
   t = a.x / a.y; d = a.x * t + a.y; return make_double2(t / d, -1. / d);
 }
+__device__ __forceinline__ float shfl_t(float v, int src) { return __shfl_sync(0xffffffffu, v, src); }
+__device__ __forceinline__ double shfl_t(double v, int src) { return __shfl_sync(0xffffffffu, v, src); }
+__device__ __forceinline__ float2 shfl_t(float2 v, int src) { return make_float2(__shfl_sync(0xffffffffu, v.x, src), __shfl_sync(0xffffffffu, v.y, src)); }
+__device__ __forceinline__ double2 shfl_t(double2 v, int src) { return make_double2(__shfl_sync(0xffffffffu, v.x, src), __shfl_sync(0xffffffffu, v.y, src)); }
 
-// Canonical problem per right-hand side: L y = alpha*b with L lower triangular n x n (n <= TS_NB).
+// Canonical problem per right-hand side: L y = alpha*b with L lower triangular n x n (n <= NB).
 //   Left : vectors are the columns of B, Tm = op(A)
 //   Right: vectors are the rows of B,    Tm = op(A)^T
 // If Tm is upper triangular the index order is reversed (rev) so the solve is always forward.
-template <typename T>
-__global__ void __launch_bounds__(TS_VEC)
+// Replaces ATL_utrsm / ATL_ntrsm (Clint/trsm-micro.base:1372-2023, Students/trsm-nano.base:206):
+// the triangle sits in shared memory column by column with every flag folded into the load, a CTA
+// solves 64 right-hand sides, four threads per right-hand side own the rows i = q (mod 4).
+// Column-oriented substitution: when x[l] is final its owner broadcasts it by shuffle and every
+// thread updates its own rows - the dependent chain is n (shuffle + FMA) steps, not n^2/2 FMAs.
+template <typename T, int NB>
+__global__ void __launch_bounds__(TS_VEC * TS_Q)
 trsm_base_kernel(int left, int tt /*Tm(i,l) = tt ? A[l+i*lda] : A[i+l*lda]*/, int cj, int unit, int rev, int n, int nvec,
                  T alpha, const T* __restrict__ A, size_t lda, T* __restrict__ B, size_t ldb, const int* abort_flag) {
   using S = ST<T>;
+  constexpr int RP = NB / TS_Q;            // rows per thread
   if (abort_flag && *abort_flag) return;
-  __shared__ T Ls[TS_NB][TS_NB + 1];
-  for (int idx = threadIdx.x; idx < TS_NB * TS_NB; idx += TS_VEC) {
-    const int i = idx / TS_NB, l = idx % TS_NB;   // canonical indices
-    T v = S::zero();
-    if (i < n && l <= i) {
-      const int ri = rev ? n - 1 - i : i, rl = rev ? n - 1 - l : l;
-      if (i == l && unit) v = S::one();
-      else {
+  __shared__ T Lc[NB][NB + 1];             // Lc[l][i] = L(i,l): column l contiguous in i
+  __shared__ T Dinv[NB];                   // reciprocal diagonal (non-unit)
+  {
+    constexpr int PER = NB * NB / (TS_VEC * TS_Q);
+    T tv[PER > 0 ? PER : 1];
+#pragma unroll
+    for (int u = 0; u < PER; u++) {
+      const int idx = threadIdx.x + u * TS_VEC * TS_Q;
+      const int i = idx % NB, l = idx / NB;    // canonical row i, column l
+      T v = S::zero();
+      if (i < n && l <= i && !(i == l && unit)) {
+        const int ri = rev ? n - 1 - i : i, rl = rev ? n - 1 - l : l;
         v = tt ? A[(size_t)rl + (size_t)ri * lda] : A[(size_t)ri + (size_t)rl * lda];
-        if (cj) v = S::conj(v);
       }
+      tv[u] = v;
     }
-    Ls[i][l] = v;
+#pragma unroll
+    for (int u = 0; u < PER; u++) {
+      const int idx = threadIdx.x + u * TS_VEC * TS_Q;
+      const int i = idx % NB, l = idx / NB;
+      T v = tv[u];
+      if (cj) v = S::conj(v);
+      Lc[l][i] = v;
+      if (i == l) Dinv[i] = (unit || i >= n) ? S::one() : s_recip<T>(v);
+    }
   }
   __syncthreads();
-  const int v = blockIdx.x * TS_VEC + threadIdx.x;
-  if (v >= nvec) return;
-  T* bp = left ? B + (size_t)v * ldb : B + v;
+  const int q = threadIdx.x & (TS_Q - 1);
+  const int grp = threadIdx.x >> 2;
+  const int v = blockIdx.x * TS_VEC + grp;
+  const bool live = v < nvec;
+  T* bp = left ? B + (size_t)(live ? v : 0) * ldb : B + (live ? v : 0);
   const size_t estride = left ? 1 : ldb;
-  T x[TS_NB];
+  T x[RP];
 #pragma unroll
-  for (int i = 0; i < TS_NB; i++) {
-    if (i < n) {
+  for (int m = 0; m < RP; m++) {
+    const int i = m * TS_Q + q;
+    x[m] = S::zero();
+    if (live && i < n) {
       const int ri = rev ? n - 1 - i : i;
-      x[i] = S::mul(alpha, bp[(size_t)ri * estride]);
-    } else x[i] = S::zero();
+      x[m] = S::mul(alpha, bp[(size_t)ri * estride]);
+    }
   }
+  const int lane_base = (threadIdx.x & 31) & ~(TS_Q - 1);
 #pragma unroll
-  for (int i = 0; i < TS_NB; i++) {
-    if (i < n) {
-      T t = x[i];
+  for (int l = 0; l < NB; l++) {
+    if (l < n) {                                   // uniform
+      // owner of row l finalises it and broadcasts to its group
+      T xl = x[l / TS_Q];
+      if (!unit) xl = S::mul(xl, Dinv[l]);
+      xl = shfl_t(xl, lane_base + (l % TS_Q));
+      if (q == (l % TS_Q)) x[l / TS_Q] = xl;
 #pragma unroll
-      for (int l = 0; l < i; l++) t = S::sub(t, S::mul(Ls[i][l], x[l]));
-      if (!unit) t = S::mul(t, s_recip<T>(Ls[i][i]));
-      x[i] = t;
+      for (int m = l / TS_Q; m < RP; m++) {
+        const int i = m * TS_Q + q;
+        if (i > l) x[m] = S::sub(x[m], S::mul(Lc[l][i], xl));   // rows >= n hold zeros in Lc
+      }
     }
   }
 #pragma unroll
-  for (int i = 0; i < TS_NB; i++) {
-    if (i < n) {
+  for (int m = 0; m < RP; m++) {
+    const int i = m * TS_Q + q;
+    if (live && i < n) {
       const int ri = rev ? n - 1 - i : i;
-      bp[(size_t)ri * estride] = x[i];
+      bp[(size_t)ri * estride] = x[m];
     }
   }
 }
@@ -229,8 +265,14 @@ static void trsm_base(int side, int uplo, int trans, int diag, int M, int N, T a
   const int tt = left ? is_tr(trans) : !is_tr(trans);
   const bool tm_lower = (uplo == Lower) != (tt != 0);
   const int grid = (nvec + TS_VEC - 1) / TS_VEC;
-  trsm_base_kernel<T><<<grid, TS_VEC, 0, current_stream()>>>(left, tt, S::cplx ? is_cj(trans) : 0, diag == Unit, !tm_lower, n, nvec,
-                                                            alpha, A, lda, B, ldb, abort_flag);
+  const int cjf = S::cplx ? is_cj(trans) : 0, un = (diag == Unit), rev = !tm_lower;
+  cudaStream_t st = current_stream();
+  constexpr int TH = TS_VEC * TS_Q;
+  // the register block is sized to the triangle: no work on padding rows
+  if (n <= 16) trsm_base_kernel<T, 16><<<grid, TH, 0, st>>>(left, tt, cjf, un, rev, n, nvec, alpha, A, lda, B, ldb, abort_flag);
+  else if (n <= 32 || TsNB<T>::V == 32)
+    trsm_base_kernel<T, 32><<<grid, TH, 0, st>>>(left, tt, cjf, un, rev, n, nvec, alpha, A, lda, B, ldb, abort_flag);
+  else trsm_base_kernel<T, TsNB<T>::V><<<grid, TH, 0, st>>>(left, tt, cjf, un, rev, n, nvec, alpha, A, lda, B, ldb, abort_flag);
   count_launch();
   AB_CUDA_CHECK(cudaGetLastError());
 }
@@ -240,6 +282,7 @@ static void trsm_rec(int side, int uplo, int trans, int diag, int M, int N, T al
                      const int* abort_flag) {
   using S = ST<T>;
   const int n = (side == Left) ? M : N;
+  constexpr int TS_NB = TsNB<T>::V;
   if (n <= TS_NB) { trsm_base<T>(side, uplo, trans, diag, M, N, alpha, A, lda, B, ldb, abort_flag); return; }
   const int n1 = tri_split(n, TS_NB), n2 = n - n1;
   const bool eff_lower = (uplo == Lower) != is_tr(trans);

@@ -23,3 +23,18 @@ for it in range(2):
     info = ab.clapack_dgetrf(ab.CblasColMajor, n, n, W, n, piv) if what == "getrf" else ab.clapack_dpotrf(ab.CblasColMajor, ab.CblasLower, n, W, n)
     e1.record(); torch.cuda.synchronize()
     print(f"{what} n={n} iter {it}: {e0.elapsed_time(e1):.3f} ms info={info} launches={ab.launch_count()}")
+# host enqueue time (async device-level entry point): is the factorisation launch-bound?
+import ctypes, time
+L = ab.lib()
+L.atlb200_dgetrf_dev.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p, ctypes.c_void_p]
+L.atlb200_dgetrf_dev.restype = None
+dinfo = torch.zeros(1, dtype=torch.int32, device=dev)
+if what == "getrf":
+    for it in range(2):
+        W.copy_(A0); torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        L.atlb200_dgetrf_dev(n, n, W.data_ptr(), n, piv.data_ptr(), dinfo.data_ptr())
+        t1 = time.perf_counter()
+        torch.cuda.synchronize()
+        t2 = time.perf_counter()
+        print(f"getrf n={n} async: host enqueue {1e3*(t1-t0):.2f} ms, total {1e3*(t2-t0):.2f} ms")
