@@ -23,6 +23,7 @@
 #include "dgemm_tma.h"
 #include <cfloat>
 #include <type_traits>
+#include <vector>
 
 namespace ab {
 
@@ -457,6 +458,11 @@ static void getrf_lookahead(int M, int N, T* A, size_t lda, int* d_ipiv, int* d_
   cudaStream_t U = current_stream(), P = ss.st;
   // SMs of one GPC are kept free of update-GEMM CTAs while a panel is being factored beside it
   const unsigned long long* reserved = env_int("ATLB200_LU_RESERVE", 1) ? cluster_reserved_mask() : nullptr;
+  // ATLB200_LU_TRACE=1: time both streams per block step with events and print the timeline (debug)
+  const bool trace = env_int("ATLB200_LU_TRACE", 0) != 0;
+  std::vector<cudaEvent_t> tev;
+  auto mark = [&](cudaStream_t st) { if (trace) { cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, st); tev.push_back(e); } };
+  mark(U);
 
   getrf_rec<T>(A, lda, 0, M, min(NB, N), d_ipiv, d_info);           // panel 0 on the main stream
   for (int k0 = 0, k = 0; k0 < MN; k0 += NB, k++) {
@@ -471,16 +477,31 @@ static void getrf_lookahead(int M, int N, T* A, size_t lda, int* d_ipiv, int* d_
         AB_CUDA_CHECK(cudaEventRecord(ss.cols[k & 1], U));
         AB_CUDA_CHECK(cudaStreamWaitEvent(P, ss.cols[k & 1], 0));
         set_current_stream(P);
+        mark(P);
         getrf_rec<T>(A, lda, c1, M - c1, w1, d_ipiv, d_info);         // panel k+1 beside the update
+        mark(P);
         AB_CUDA_CHECK(cudaEventRecord(ss.panel[k & 1], P));
         set_current_stream(U);
         set_gemm_reserved(reserved);                                   // leave a GPC to the panel kernels
       }
+      if (more) mark(U);
       lu_apply_panel<T>(A, lda, M, k0, w, c1 + w1, nright - w1, d_ipiv);
+      if (more) mark(U);
       set_gemm_reserved(nullptr);
     }
     if (k0 > 0) laswp<T>(k0, A, lda, k0, k0 + w, d_ipiv, 1);           // interchanges left of the panel
     if (more && nright > 0) AB_CUDA_CHECK(cudaStreamWaitEvent(U, ss.panel[k & 1], 0));
+  }
+  if (trace) {
+    AB_CUDA_CHECK(cudaDeviceSynchronize());
+    fprintf(stderr, "# getrf look-ahead trace M=%d N=%d NB=%d: step, panel(k+1) start..end [ms], update(rest) start..end [ms]\n", M, N, NB);
+    for (size_t i = 1; i + 3 < tev.size(); i += 4) {
+      float a, b, c, d;
+      cudaEventElapsedTime(&a, tev[0], tev[i]); cudaEventElapsedTime(&b, tev[0], tev[i + 1]);
+      cudaEventElapsedTime(&c, tev[0], tev[i + 2]); cudaEventElapsedTime(&d, tev[0], tev[i + 3]);
+      fprintf(stderr, "%3zu  P %8.3f .. %8.3f (%6.3f)   U %8.3f .. %8.3f (%6.3f)\n", i / 4, a, b, b - a, c, d, d - c);
+    }
+    for (auto e : tev) cudaEventDestroy(e);
   }
 }
 
@@ -488,7 +509,7 @@ template <typename T>
 void getrf(int M, int N, T* A, size_t lda, int* d_ipiv, int* d_info) {
   AB_CUDA_CHECK(cudaMemsetAsync(d_info, 0, sizeof(int), current_stream()));
   if (M <= 0 || N <= 0) return;
-  const int NB = env_int("ATLB200_LU_NB", 256);
+  const int NB = env_int("ATLB200_LU_NB", 512);
   if (env_int("ATLB200_LU_LOOKAHEAD", 1) && NB > 0 && min(M, N) >= 4 * NB) getrf_lookahead<T>(M, N, A, lda, d_ipiv, d_info, NB);
   else getrf_rec<T>(A, lda, 0, M, N, d_ipiv, d_info);
 }
@@ -588,10 +609,70 @@ static void potrf_rec(int uplo, int N, T* A, size_t lda, int* d_info, int off) {
   }
 }
 
+// Right-looking blocked Cholesky with look-ahead (same idea as getrf_lookahead): the next block
+// column (row, for Upper) receives update k first and is factored on the side stream while the
+// main stream applies update k to the rest of the trailing triangle.  d_info doubles as the abort
+// flag of every kernel, so the reference's stop-at-first-failure semantics are unchanged.
+template <typename T>
+static void potrf_lookahead(int uplo, int N, T* A, size_t lda, int* d_info, int NB) {
+  using S = ST<T>;
+  using R = typename S::real;
+  SideStream& ss = g_side;
+  ss.ensure();
+  cudaStream_t U = current_stream(), P = ss.st;
+  const unsigned long long* reserved = env_int("ATLB200_LU_RESERVE", 1) ? cluster_reserved_mask() : nullptr;
+  const int tr = S::cplx ? ConjTrans : TransT;
+  const bool lower = (uplo == Lower);
+  auto rank_k = [&](int n, int k, const T* X, T* Cd) {      // Cd(tri) -= X X^H (Lower: X is n x k) or X^H X (Upper: X is k x n)
+    if constexpr (S::cplx) herk<T>(uplo, lower ? NoTrans : ConjTrans, n, k, (R)-1, X, lda, (R)1, Cd, lda, d_info);
+    else syrk<T>(uplo, lower ? NoTrans : TransT, n, k, S::from_real(-1), X, lda, S::one(), Cd, lda, d_info);
+  };
+  auto factor_panel = [&](int k0, int w) {
+    T* Akk = A + (size_t)k0 + (size_t)k0 * lda;
+    potrf_rec<T>(uplo, w, Akk, lda, d_info, k0);
+    const int rest = N - k0 - w;
+    if (rest > 0) {
+      if (lower) trsm<T>(Right, Lower, tr, NonUnit, rest, w, S::one(), Akk, lda, Akk + w, lda, d_info);
+      else trsm<T>(Left, Upper, tr, NonUnit, w, rest, S::one(), Akk, lda, Akk + (size_t)w * lda, lda, d_info);
+    }
+  };
+  factor_panel(0, min(NB, N));
+  for (int k0 = 0, k = 0; k0 < N; k0 += NB, k++) {
+    const int w = min(NB, N - k0), c1 = k0 + w, rest = N - c1;
+    if (rest <= 0) break;
+    const int w1 = min(NB, rest);
+    // factored panel below / right of the diagonal block
+    const T* X = lower ? A + (size_t)c1 + (size_t)k0 * lda : A + (size_t)k0 + (size_t)c1 * lda;
+    T* Ann = A + (size_t)c1 + (size_t)c1 * lda;
+    // ---- next panel first
+    rank_k(w1, w, X, Ann);
+    if (rest > w1) {
+      if (lower) gemm<T>(NoTrans, tr, rest - w1, w1, w, S::from_real(-1), X + w1, lda, X, lda, S::one(), Ann + w1, lda, d_info);
+      else gemm<T>(tr, NoTrans, w1, rest - w1, w, S::from_real(-1), X, lda, X + (size_t)w1 * lda, lda, S::one(), Ann + (size_t)w1 * lda, lda, d_info);
+    }
+    AB_CUDA_CHECK(cudaEventRecord(ss.cols[k & 1], U));
+    AB_CUDA_CHECK(cudaStreamWaitEvent(P, ss.cols[k & 1], 0));
+    set_current_stream(P);
+    factor_panel(c1, w1);
+    AB_CUDA_CHECK(cudaEventRecord(ss.panel[k & 1], P));
+    set_current_stream(U);
+    // ---- the rest of the trailing triangle beside it
+    if (rest > w1) {
+      set_gemm_reserved(reserved);
+      const T* X2 = lower ? X + w1 : X + (size_t)w1 * lda;
+      rank_k(rest - w1, w, X2, Ann + (size_t)w1 + (size_t)w1 * lda);
+      set_gemm_reserved(nullptr);
+    }
+    AB_CUDA_CHECK(cudaStreamWaitEvent(U, ss.panel[k & 1], 0));
+  }
+}
+
 template <typename T>
 void potrf(int uplo, int N, T* A, size_t lda, int* d_info) {
   AB_CUDA_CHECK(cudaMemsetAsync(d_info, 0, sizeof(int), current_stream()));
-  potrf_rec<T>(uplo, N, A, lda, d_info, 0);
+  const int NB = env_int("ATLB200_LLT_NB", 512);
+  if (env_int("ATLB200_LU_LOOKAHEAD", 1) && NB > 0 && N >= 4 * NB) potrf_lookahead<T>(uplo, N, A, lda, d_info, NB);
+  else potrf_rec<T>(uplo, N, A, lda, d_info, 0);
 }
 
 #define AB_INST(T)                                                    \

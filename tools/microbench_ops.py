@@ -49,3 +49,15 @@ for nn in (32,):
     S = torch.eye(nn, device=dev, dtype=torch.float64) * 4 + 0.01
     S0 = S.clone()
     timed(f"potrf leaf n={nn} (+copy)", lambda: (S.copy_(S0), ops.potrf(ab.CblasLower, nn, S.data_ptr(), nn, info)))
+# whole panel chains (what the look-ahead side stream runs per block step)
+for M in (16384, 8192, 2048):
+    for w in (256, 512):
+        Wp = torch.rand((w, M), device=dev, dtype=torch.float64) - 0.5
+        W0 = Wp.clone()
+        timed(f"getrf panel M={M} w={w} (recursive, +copy)", lambda: (Wp.copy_(W0), ops.getrf(M, w, Wp.data_ptr(), M, piv, info)))
+for w in (256, 512):
+    S = torch.rand((w, w), device=dev, dtype=torch.float64) * 0.01 + torch.eye(w, device=dev, dtype=torch.float64) * 4
+    S0 = S.clone()
+    timed(f"potrf diag block n={w} (recursive, +copy)", lambda: (S.copy_(S0), ops.potrf(ab.CblasLower, w, S.data_ptr(), w, info)))
+    timed(f"trsm R,L,T,N n={w} nrhs=16384 (panel below diag)", lambda: ops.trsm(ab.CblasRight, ab.CblasLower, ab.CblasTrans, ab.CblasNonUnit, 16384 - w, w, 1.0, A.data_ptr(), n, B.data_ptr(), n))
+    timed(f"trsm L,L,N,U n={w} nrhs=16384 (U block row)", lambda: ops.trsm(ab.CblasLeft, ab.CblasLower, ab.CblasNoTrans, ab.CblasUnit, w, 16384 - w, 1.0, A.data_ptr(), n, B.data_ptr(), n))
