@@ -12,6 +12,7 @@
 #include "ab_api.h"
 #include "gemm_generic.cuh"
 #include "dgemm_tma.h"
+#include "zgemm_tma.h"
 #include <type_traits>
 
 namespace ab {
@@ -37,6 +38,11 @@ static void gemm_flags(int ta, int ca, int tb, int cb, int M, int N, int K, T al
   if constexpr (std::is_same<T, double>::value) {
     if ((double)M * N * K >= 262144.0 && !herk &&
         dgemm_tma(ta, tb, M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, cmode, abort_flag))
+      return;
+  }
+  if constexpr (std::is_same<T, double2>::value) {
+    if ((double)M * N * K >= 65536.0 &&
+        zgemm_tma(ta, p.ca, tb, p.cb, M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, cmode, herk, abort_flag))
       return;
   }
   gemm_generic_launch(p);
