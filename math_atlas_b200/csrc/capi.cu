@@ -20,6 +20,7 @@
 #include <cctype>
 #include <mutex>
 #include <memory>
+#include <algorithm>
 
 using namespace ab;
 
@@ -153,10 +154,90 @@ struct DevInts {
 };
 
 // ------------------------------------------------------------------------------------- ATL_* level (column-major, unchecked)
+// ---- large GEMM with host operands: column-panel pipeline --------------------------------------
+// H2D of panel j+1 (B and C columns), the GEMM of panel j and the D2H of panel j-1 run on three
+// streams, so PCIe traffic hides behind the tensor pipe (the reference has no such stage: its
+// operands are already in host memory; this is the cost of the host-pointer drop-in).
+namespace {
+struct CopyStreams {
+  cudaStream_t h2d = nullptr, d2h = nullptr;
+  static constexpr int NEV = 64;
+  cudaEvent_t in[NEV], done[NEV], a_in = nullptr, start = nullptr;
+  int dev = -1;
+  void ensure() {
+    int d; AB_CUDA_CHECK(cudaGetDevice(&d));
+    if (h2d && d == dev) return;
+    dev = d;
+    AB_CUDA_CHECK(cudaStreamCreateWithFlags(&h2d, cudaStreamNonBlocking));
+    AB_CUDA_CHECK(cudaStreamCreateWithFlags(&d2h, cudaStreamNonBlocking));
+    for (int i = 0; i < NEV; i++) {
+      AB_CUDA_CHECK(cudaEventCreateWithFlags(&in[i], cudaEventDisableTiming));
+      AB_CUDA_CHECK(cudaEventCreateWithFlags(&done[i], cudaEventDisableTiming));
+    }
+    AB_CUDA_CHECK(cudaEventCreateWithFlags(&a_in, cudaEventDisableTiming));
+    AB_CUDA_CHECK(cudaEventCreateWithFlags(&start, cudaEventDisableTiming));
+  }
+};
+thread_local CopyStreams g_copy;
+}  // namespace
+
+template <typename T>
+static bool atl_gemm_pipelined(int TA, int TB, size_t M, size_t N, size_t K, T alpha, const T* A, size_t lda, const T* B, size_t ldb,
+                               T beta, T* C, size_t ldc) {
+  // only when C and B live on the host and the problem is big enough for panels of >= 1024 columns
+  if (g_async || is_device_ptr(C) || is_device_ptr(B)) return false;
+  if (ST<T>::is_zero(alpha) || K == 0) return false;
+  if ((double)M * N * K < 4096.0 * 4096.0 * 4096.0 || N < 4096) return false;
+  const bool tA = (TA == TransT || TA == ConjTrans), tB = (TB == TransT || TB == ConjTrans);
+  init_pool_once();
+  CopyStreams& cs = g_copy;
+  cs.ensure();
+  cudaStream_t U = current_stream();
+  const size_t esz = sizeof(T);
+  const bool beta0 = ST<T>::is_zero(beta);
+  // device images: A whole, B and C whole (filled panel by panel)
+  Operand<T> a(A, (int)(tA ? K : M), (int)(tA ? M : K), lda, false, false);   // no copy yet (done below on the copy stream)
+  const size_t ldbd = (((tB ? N : K) + 15) & ~(size_t)15), ldcd = ((M + 15) & ~(size_t)15);
+  T *dB = nullptr, *dC = nullptr;
+  AB_CUDA_CHECK(cudaMallocAsync(&dB, esz * ldbd * (tB ? K : N), U));
+  AB_CUDA_CHECK(cudaMallocAsync(&dC, esz * ldcd * N, U));
+  AB_CUDA_CHECK(cudaEventRecord(cs.start, U));
+  AB_CUDA_CHECK(cudaStreamWaitEvent(cs.h2d, cs.start, 0));
+  AB_CUDA_CHECK(cudaStreamWaitEvent(cs.d2h, cs.start, 0));
+  if (a.staged)
+    AB_CUDA_CHECK(cudaMemcpy2DAsync(a.d, esz * a.ld, a.h, esz * a.ldh, esz * (size_t)a.rows, (size_t)a.cols, cudaMemcpyHostToDevice, cs.h2d));
+  AB_CUDA_CHECK(cudaEventRecord(cs.a_in, cs.h2d));
+  AB_CUDA_CHECK(cudaStreamWaitEvent(U, cs.a_in, 0));
+  int np = (int)std::min<size_t>(CopyStreams::NEV, std::max<size_t>(2, N / 2048));
+  const size_t pw = ((N + np - 1) / np + 127) / 128 * 128;   // panel width, multiple of the GEMM tile
+  np = (int)((N + pw - 1) / pw);
+  for (int j = 0; j < np; j++) {
+    const size_t c0 = (size_t)j * pw, nc = std::min(pw, N - c0);
+    // H2D of this panel's B and C columns
+    if (!tB) AB_CUDA_CHECK(cudaMemcpy2DAsync(dB + c0 * ldbd, esz * ldbd, B + c0 * ldb, esz * ldb, esz * K, nc, cudaMemcpyHostToDevice, cs.h2d));
+    else     AB_CUDA_CHECK(cudaMemcpy2DAsync(dB + c0, esz * ldbd, B + c0, esz * ldb, esz * nc, K, cudaMemcpyHostToDevice, cs.h2d));
+    if (!beta0) AB_CUDA_CHECK(cudaMemcpy2DAsync(dC + c0 * ldcd, esz * ldcd, C + c0 * ldc, esz * ldc, esz * M, nc, cudaMemcpyHostToDevice, cs.h2d));
+    AB_CUDA_CHECK(cudaEventRecord(cs.in[j], cs.h2d));
+    AB_CUDA_CHECK(cudaStreamWaitEvent(U, cs.in[j], 0));
+    gemm<T>(TA, TB, (int)M, (int)nc, (int)K, alpha, a.d, a.ld, tB ? dB + c0 : dB + c0 * ldbd, ldbd, beta, dC + c0 * ldcd, ldcd);
+    AB_CUDA_CHECK(cudaEventRecord(cs.done[j], U));
+    AB_CUDA_CHECK(cudaStreamWaitEvent(cs.d2h, cs.done[j], 0));
+    AB_CUDA_CHECK(cudaMemcpy2DAsync(C + c0 * ldc, esz * ldc, dC + c0 * ldcd, esz * ldcd, esz * M, nc, cudaMemcpyDeviceToHost, cs.d2h));
+  }
+  AB_CUDA_CHECK(cudaStreamSynchronize(cs.d2h));
+  AB_CUDA_CHECK(cudaStreamSynchronize(U));
+  AB_CUDA_CHECK(cudaFreeAsync(dB, U));
+  AB_CUDA_CHECK(cudaFreeAsync(dC, U));
+  a.finish();
+  sync_stream();
+  return true;
+}
+
 template <typename T>
 static void atl_gemm(int TA, int TB, size_t M, size_t N, size_t K, T alpha, const T* A, size_t lda, const T* B, size_t ldb,
                      T beta, T* C, size_t ldc) {
   if (M == 0 || N == 0) return;
+  if (atl_gemm_pipelined<T>(TA, TB, M, N, K, alpha, A, lda, B, ldb, beta, C, ldc)) return;
   const bool needAB = !(ST<T>::is_zero(alpha) || K == 0);
   const bool tA = (TA == TransT || TA == ConjTrans), tB = (TB == TransT || TB == ConjTrans);
   Operand<T> a(A, needAB ? (int)(tA ? K : M) : 0, needAB ? (int)(tA ? M : K) : 0, lda, true, false);
