@@ -472,6 +472,17 @@ static void getrf_lookahead(int M, int N, T* A, size_t lda, int* d_ipiv, int* d_
     const bool more = (c1 < MN);                 // is there a next panel to factor?
     if (nright > 0) {
       const int w1 = more ? min(NB, N - c1) : 0;
+      // A panel too tall for one cluster is factored by the cooperative global-barrier kernel, whose
+      // CTAs cannot become co-resident while the persistent update GEMM holds the SMs (measured:
+      // N=65536 ran 2.4x slower with the two fighting) - such steps run back to back instead.
+      bool cl;
+      (void)leaf_width_for<T>(M - c1, &cl);
+      if (more && !cl) {
+        lu_apply_panel<T>(A, lda, M, k0, w, c1, nright, d_ipiv);
+        getrf_rec<T>(A, lda, c1, M - c1, w1, d_ipiv, d_info);
+        if (k0 > 0) laswp<T>(k0, A, lda, k0, k0 + w, d_ipiv, 1);
+        continue;
+      }
       if (more) {
         lu_apply_panel<T>(A, lda, M, k0, w, c1, w1, d_ipiv);          // next panel's columns first
         AB_CUDA_CHECK(cudaEventRecord(ss.cols[k & 1], U));
