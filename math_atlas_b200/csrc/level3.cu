@@ -13,6 +13,7 @@
 #include "gemm_generic.cuh"
 #include "dgemm_tma.h"
 #include "zgemm_tma.h"
+#include "sgemm_ffma.h"
 #include <type_traits>
 
 namespace ab {
@@ -38,6 +39,16 @@ static void gemm_flags(int ta, int ca, int tb, int cb, int M, int N, int K, T al
   if constexpr (std::is_same<T, double>::value) {
     if ((double)M * N * K >= 262144.0 && !herk &&
         dgemm_tma(ta, tb, M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, cmode, abort_flag))
+      return;
+  }
+  if constexpr (std::is_same<T, float>::value) {
+    if ((double)M * N >= 128.0 * 128.0 && K >= 8 && !herk &&
+        sgemm_ffma(ta, tb, M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, cmode, abort_flag))
+      return;
+  }
+  if constexpr (std::is_same<T, float2>::value) {
+    if ((double)M * N >= 64.0 * 64.0 && K >= 8 &&
+        cgemm_ffma(ta, p.ca, tb, p.cb, M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, cmode, herk, abort_flag))
       return;
   }
   if constexpr (std::is_same<T, double2>::value) {

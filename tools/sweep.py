@@ -46,6 +46,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--quick", action="store_true")
     ap.add_argument("--what", default="gemm,l3,lapack")
+    ap.add_argument("--types", default="dszc")
     args = ap.parse_args()
     what = args.what.split(",")
     ab.lib()
@@ -53,7 +54,7 @@ def main():
     emit(kind="peak", fp64_dmma_tflops=round(peak64, 2))
     if "gemm" in what:
         sizes = [256, 512, 1024, 2048, 4096, 8192, 16384]
-        for pre in "dszc":
+        for pre in args.types:
             cm = 4 if pre in "cz" else 1
             for n in sizes:
                 if args.quick and n > 4096: continue
