@@ -9,7 +9,7 @@
 namespace ab {
 namespace {
 
-constexpr int BM = 64, BN = 64, BK = 8, THREADS = 256, PAD = 2;
+constexpr int BM = 64, BN = 64, BK = 8, THREADS = 256, GROUP_M = 32, PAD = 2;
 
 struct CParams {
   int M, N, K;
@@ -58,7 +58,12 @@ __global__ void __launch_bounds__(THREADS, 2) cgemm_ffma_kernel(const CParams p)
   if (p.abort_flag && *p.abort_flag) return;
   __shared__ __align__(16) float2 As[2][BK][BM + PAD];
   __shared__ __align__(16) float2 Bs[2][BK][BN + PAD];
-  const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
+  // grouped rasterisation: GROUP_M tile rows share their B panel in L2 (same map as dgemm_tma.cu)
+  const int tiles_m = (p.M + BM - 1) / BM, tiles_n = (p.N + BN - 1) / BN;
+  const int in_group = GROUP_M * tiles_n;
+  const int first_m = ((int)blockIdx.x / in_group) * GROUP_M;
+  const int gsz = min(tiles_m - first_m, GROUP_M);
+  const int m0 = (first_m + ((int)blockIdx.x % in_group) % gsz) * BM, n0 = (((int)blockIdx.x % in_group) / gsz) * BN;
   if (p.cmode == C_UPPER && m0 > n0 + BN - 1) return;
   if (p.cmode == C_LOWER && n0 > m0 + BM - 1) return;
   const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
@@ -137,11 +142,11 @@ bool cgemm_ffma(int ta, int ca, int tb, int cb, int M, int N, int K, float2 alph
                 size_t ldb, float2 beta, float2* C, size_t ldc, int cmode, int herk, const int* abort_flag) {
   if (M <= 0 || N <= 0 || K <= 0) return false;
   const int gx = (M + BM - 1) / BM, gy = (N + BN - 1) / BN;
-  if (gy > 65535) return false;
+  if ((long long)gx * gy > 0x7fffffffLL) return false;
   CParams p{M, N, K, A, lda, ta, ca, B, ldb, tb, cb, alpha, beta, C, ldc, cmode, herk,
             (int)(((reinterpret_cast<uintptr_t>(A) & 15) == 0) && (lda % 2 == 0)),
             (int)(((reinterpret_cast<uintptr_t>(B) & 15) == 0) && (ldb % 2 == 0)), abort_flag};
-  cgemm_ffma_kernel<<<dim3(gx, gy), THREADS, 0, current_stream()>>>(p);
+  cgemm_ffma_kernel<<<gx * gy, THREADS, 0, current_stream()>>>(p);
   count_launch();
   AB_CUDA_CHECK(cudaGetLastError());
   return true;
