@@ -32,6 +32,20 @@ template <typename T>
 void trsm(int side, int uplo, int trans, int diag, int M, int N, T alpha, const T* A, size_t lda, T* B, size_t ldb,
           const int* abort_flag = nullptr);
 
+// C <- alpha*A*B + beta*C (Left) or alpha*B*A + beta*C (Right), A symmetric (herm=0) or Hermitian
+// (herm=1) stored in one triangle          (reference ATL_Xsymm/ATL_Xhemm, Clint/l3micro.base)
+template <typename T>
+void symm(int side, int uplo, int herm, int M, int N, T alpha, const T* A, size_t lda, const T* B, size_t ldb, T beta, T* C, size_t ldc);
+
+// C(uplo) <- alpha*op(A)*op(B)^T + alpha*op(B)*op(A)^T + beta*C    (reference ATL_Xsyr2k)
+template <typename T>
+void syr2k(int uplo, int trans, int N, int K, T alpha, const T* A, size_t lda, const T* B, size_t ldb, T beta, T* C, size_t ldc);
+
+// C(uplo) <- alpha*op(A)*op(B)^H + conj(alpha)*op(B)*op(A)^H + beta*C, beta real   (reference ATL_Xher2k)
+template <typename T>
+void her2k(int uplo, int trans, int N, int K, T alpha, const T* A, size_t lda, const T* B, size_t ldb, typename ST<T>::real beta,
+           T* C, size_t ldc);
+
 // Row interchanges (reference ATL_laswp, Clint/atlas-lp.base:1053); piv is a DEVICE array here.
 template <typename T>
 void laswp(int N, T* A, size_t lda, int K1, int K2, const int* d_piv, int inci);

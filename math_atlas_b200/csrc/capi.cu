@@ -689,3 +689,141 @@ void atlb200_set_async(int on) { g_async = on; }
     laswp<T>(N, MP(T, A), lda, K1, K2, d_piv, inci); }
 DEV_API(s, float) DEV_API(d, double) DEV_API(c, cfloat) DEV_API(z, cdouble)
 }
+
+// ------------------------------------------------------------------------------------- SYMM / HEMM / SYR2K / HER2K
+// the rest of the level-3 BLAS (reference Clint/cblas.base:237-586).
+template <typename T>
+static void atl_symm(int herm, int side, int uplo, size_t M, size_t N, T alpha, const T* A, size_t lda, const T* B, size_t ldb,
+                     T beta, T* C, size_t ldc) {
+  if (M == 0 || N == 0) return;
+  const bool need = !ST<T>::is_zero(alpha);
+  const int nA = (int)(side == Left ? M : N);
+  Operand<T> a(A, need ? nA : 0, need ? nA : 0, lda, true, false);
+  Operand<T> b(B, need ? (int)M : 0, need ? (int)N : 0, ldb, true, false);
+  Operand<T> c(C, (int)M, (int)N, ldc, !ST<T>::is_zero(beta), true);
+  symm<T>(side, uplo, herm, (int)M, (int)N, alpha, a.d, a.ld, b.d, b.ld, beta, c.d, c.ld);
+  a.finish(); b.finish(); c.finish();
+  sync_stream();
+}
+template <typename T>
+static void atl_syr2k(int uplo, int trans, size_t N, size_t K, T alpha, const T* A, size_t lda, const T* B, size_t ldb, T beta,
+                      T* C, size_t ldc) {
+  if (N == 0) return;
+  const bool need = !(ST<T>::is_zero(alpha) || K == 0);
+  const bool t = (trans != NoTrans);
+  Operand<T> a(A, need ? (int)(t ? K : N) : 0, need ? (int)(t ? N : K) : 0, lda, true, false);
+  Operand<T> b(B, need ? (int)(t ? K : N) : 0, need ? (int)(t ? N : K) : 0, ldb, true, false);
+  Operand<T> c(C, (int)N, (int)N, ldc, true, true);
+  syr2k<T>(uplo, trans, (int)N, (int)K, alpha, a.d, a.ld, b.d, b.ld, beta, c.d, c.ld);
+  a.finish(); b.finish(); c.finish();
+  sync_stream();
+}
+template <typename T>
+static void atl_her2k(int uplo, int trans, size_t N, size_t K, T alpha, const T* A, size_t lda, const T* B, size_t ldb,
+                      typename ST<T>::real beta, T* C, size_t ldc) {
+  if (N == 0) return;
+  const bool need = !(ST<T>::is_zero(alpha) || K == 0);
+  const bool t = (trans != NoTrans);
+  Operand<T> a(A, need ? (int)(t ? K : N) : 0, need ? (int)(t ? N : K) : 0, lda, true, false);
+  Operand<T> b(B, need ? (int)(t ? K : N) : 0, need ? (int)(t ? N : K) : 0, ldb, true, false);
+  Operand<T> c(C, (int)N, (int)N, ldc, true, true);
+  her2k<T>(uplo, trans, (int)N, (int)K, alpha, a.d, a.ld, b.d, b.ld, beta, c.d, c.ld);
+  a.finish(); b.finish(); c.finish();
+  sync_stream();
+}
+
+template <typename T>
+static void cb_symm(const char* rout, int herm, int Order, int Side, int Uplo, int M, int N, T alpha, const T* A, int lda, const T* B,
+                    int ldb, T beta, T* C, int ldc) {
+  int info = 2000;
+  if (Order == ColMajor || Order == RowMajor) {
+    const bool col = (Order == ColMajor);
+    if (Side == Left) { if (lda < M || lda < 1) info = cblas_errprn(8, info, "lda must be >= MAX(M,1): lda=%d M=%d", lda, M); }
+    else if (Side == Right) { if (lda < N || lda < 1) info = cblas_errprn(8, info, "lda must be >= MAX(N,1): lda=%d N=%d", lda, N); }
+    else info = cblas_errprn(2, info, "SIDE must be %d or %d, but is set to %d", Right, Left, Side);
+    const int req = col ? M : N;
+    if (ldb < req || ldb < 1) info = cblas_errprn(10, info, "ldb must be >= MAX(%c,1): ldb=%d %c=%d", col ? 'M' : 'N', ldb, col ? 'M' : 'N', req);
+    if (ldc < req || ldc < 1) info = cblas_errprn(13, info, "ldc must be >= MAX(%c,1): ldc=%d %c=%d", col ? 'M' : 'N', ldc, col ? 'M' : 'N', req);
+  } else info = cblas_errprn(1, info, "Order must be %d or %d, but is set to %d", RowMajor, ColMajor, Order);
+  if (Uplo != Upper && Uplo != Lower) info = cblas_errprn(3, info, "UPLO must be %d or %d, but is set to %d", Upper, Lower, Uplo);
+  if (M < 0) info = cblas_errprn(4, info, "M cannot be less than zero; it is set to %d.", M);
+  if (N < 0) info = cblas_errprn(5, info, "N cannot be less than zero; it is set to %d.", N);
+  if (info != 2000) { cblas_xerbla(info, rout, ""); return; }
+  if (Order == ColMajor) atl_symm<T>(herm, Side, Uplo, M, N, alpha, A, lda, B, ldb, beta, C, ldc);
+  else atl_symm<T>(herm, Side == Left ? Right : Left, Uplo == Upper ? Lower : Upper, N, M, alpha, A, lda, B, ldb, beta, C, ldc);
+}
+static bool check_syr2k(const char* rout, bool her, int Order, int Uplo, int Trans, int N, int K, int lda, int ldb, int ldc) {
+  int info = 2000;
+  if (Uplo != Upper && Uplo != Lower) info = cblas_errprn(2, info, "UPLO must be %d or %d, but is set to %d", Upper, Lower, Uplo);
+  if (N < 0) info = cblas_errprn(4, info, "N cannot be less than zero; it is set to %d.", N);
+  if (K < 0) info = cblas_errprn(5, info, "K cannot be less than zero; it is set to %d.", K);
+  if (Order == ColMajor || Order == RowMajor) {
+    const bool nt = (Trans == NoTrans);
+    if (!nt) {
+      const bool ok = her ? (Trans == ConjTrans) : (Trans == TransT || Trans == ConjTrans);
+      if (!ok) info = cblas_errprn(3, info, "Trans must be %d or %d, but is set to %d", NoTrans, her ? ConjTrans : TransT, Trans);
+    }
+    const int req = ((Order == ColMajor) == nt) ? N : K;
+    const char nm = ((Order == ColMajor) == nt) ? 'N' : 'K';
+    if (lda < req || lda < 1) info = cblas_errprn(8, info, "lda must be >= MAX(%c,1): lda=%d %c=%d", nm, lda, nm, req);
+    if (ldb < req || ldb < 1) info = cblas_errprn(10, info, "ldb must be >= MAX(%c,1): ldb=%d %c=%d", nm, ldb, nm, req);
+  } else info = cblas_errprn(1, info, "Order must be %d or %d, but is set to %d", RowMajor, ColMajor, Order);
+  if (ldc < N || ldc < 1) info = cblas_errprn(13, info, "ldc must be >= MAX(N,1): ldc=%d N=%d", ldc, N);
+  if (info != 2000) { cblas_xerbla(info, rout, ""); return false; }
+  return true;
+}
+template <typename T>
+static void cb_syr2k(const char* rout, int Order, int Uplo, int Trans, int N, int K, T alpha, const T* A, int lda, const T* B, int ldb,
+                     T beta, T* C, int ldc) {
+  if (!check_syr2k(rout, false, Order, Uplo, Trans, N, K, lda, ldb, ldc)) return;
+  if (Order == ColMajor) atl_syr2k<T>(Uplo, Trans, N, K, alpha, A, lda, B, ldb, beta, C, ldc);
+  else atl_syr2k<T>(Uplo == Upper ? Lower : Upper, Trans == NoTrans ? TransT : NoTrans, N, K, alpha, A, lda, B, ldb, beta, C, ldc);
+}
+template <typename T>
+static void cb_her2k(const char* rout, int Order, int Uplo, int Trans, int N, int K, T alpha, const T* A, int lda, const T* B, int ldb,
+                     typename ST<T>::real beta, T* C, int ldc) {
+  if (!check_syr2k(rout, true, Order, Uplo, Trans, N, K, lda, ldb, ldc)) return;
+  if (Order == ColMajor) atl_her2k<T>(Uplo, Trans, N, K, alpha, A, lda, B, ldb, beta, C, ldc);
+  else atl_her2k<T>(Uplo == Upper ? Lower : Upper, Trans == NoTrans ? ConjTrans : NoTrans, N, K, ST<T>::conj(alpha), A, lda, B, ldb, beta, C, ldc);
+}
+
+extern "C" {
+#define REAL_L3X(P, T)                                                                                                         \
+  void cblas_##P##symm(int Order, int Side, int Uplo, int M, int N, T alpha, const T* A, int lda, const T* B, int ldb, T beta, \
+                       T* C, int ldc) { cb_symm<T>("cblas_" #P "symm", 0, Order, Side, Uplo, M, N, alpha, A, lda, B, ldb, beta, C, ldc); } \
+  void cblas_##P##syr2k(int Order, int Uplo, int Trans, int N, int K, T alpha, const T* A, int lda, const T* B, int ldb,       \
+                        T beta, T* C, int ldc) { cb_syr2k<T>("cblas_" #P "syr2k", Order, Uplo, Trans, N, K, alpha, A, lda, B, ldb, beta, C, ldc); } \
+  void ATL_##P##symm(int Side, int Uplo, size_t M, size_t N, T alpha, const T* A, size_t lda, const T* B, size_t ldb, T beta,  \
+                     T* C, size_t ldc) { atl_symm<T>(0, Side, Uplo, M, N, alpha, A, lda, B, ldb, beta, C, ldc); }              \
+  void ATL_##P##syr2k(int Uplo, int Trans, size_t N, size_t K, T alpha, const T* A, size_t lda, const T* B, size_t ldb,        \
+                      T beta, T* C, size_t ldc) { atl_syr2k<T>(Uplo, Trans, N, K, alpha, A, lda, B, ldb, beta, C, ldc); }
+REAL_L3X(s, float)
+REAL_L3X(d, double)
+#define CPLX_L3X(P, T, R)                                                                                                      \
+  void cblas_##P##symm(int Order, int Side, int Uplo, int M, int N, const void* alpha, const void* A, int lda, const void* B,  \
+                       int ldb, const void* beta, void* C, int ldc) {                                                         \
+    cb_symm<T>("cblas_" #P "symm", 0, Order, Side, Uplo, M, N, CS(T, alpha), CP(T, A), lda, CP(T, B), ldb, CS(T, beta), MP(T, C), ldc); } \
+  void cblas_##P##hemm(int Order, int Side, int Uplo, int M, int N, const void* alpha, const void* A, int lda, const void* B,  \
+                       int ldb, const void* beta, void* C, int ldc) {                                                         \
+    cb_symm<T>("cblas_" #P "hemm", 1, Order, Side, Uplo, M, N, CS(T, alpha), CP(T, A), lda, CP(T, B), ldb, CS(T, beta), MP(T, C), ldc); } \
+  void cblas_##P##syr2k(int Order, int Uplo, int Trans, int N, int K, const void* alpha, const void* A, int lda,               \
+                        const void* B, int ldb, const void* beta, void* C, int ldc) {                                         \
+    cb_syr2k<T>("cblas_" #P "syr2k", Order, Uplo, Trans, N, K, CS(T, alpha), CP(T, A), lda, CP(T, B), ldb, CS(T, beta), MP(T, C), ldc); } \
+  void cblas_##P##her2k(int Order, int Uplo, int Trans, int N, int K, const void* alpha, const void* A, int lda,               \
+                        const void* B, int ldb, R beta, void* C, int ldc) {                                                   \
+    cb_her2k<T>("cblas_" #P "her2k", Order, Uplo, Trans, N, K, CS(T, alpha), CP(T, A), lda, CP(T, B), ldb, beta, MP(T, C), ldc); } \
+  void ATL_##P##symm(int Side, int Uplo, size_t M, size_t N, const R* alpha, const R* A, size_t lda, const R* B, size_t ldb,   \
+                     const R* beta, R* C, size_t ldc) {                                                                       \
+    atl_symm<T>(0, Side, Uplo, M, N, CS(T, alpha), CP(T, A), lda, CP(T, B), ldb, CS(T, beta), MP(T, C), ldc); }                \
+  void ATL_##P##hemm(int Side, int Uplo, size_t M, size_t N, const R* alpha, const R* A, size_t lda, const R* B, size_t ldb,   \
+                     const R* beta, R* C, size_t ldc) {                                                                       \
+    atl_symm<T>(1, Side, Uplo, M, N, CS(T, alpha), CP(T, A), lda, CP(T, B), ldb, CS(T, beta), MP(T, C), ldc); }                \
+  void ATL_##P##syr2k(int Uplo, int Trans, size_t N, size_t K, const R* alpha, const R* A, size_t lda, const R* B, size_t ldb, \
+                      const R* beta, R* C, size_t ldc) {                                                                      \
+    atl_syr2k<T>(Uplo, Trans, N, K, CS(T, alpha), CP(T, A), lda, CP(T, B), ldb, CS(T, beta), MP(T, C), ldc); }                 \
+  void ATL_##P##her2k(int Uplo, int Trans, size_t N, size_t K, const R* alpha, const R* A, size_t lda, const R* B, size_t ldb, \
+                      R beta, R* C, size_t ldc) {                                                                             \
+    atl_her2k<T>(Uplo, Trans, N, K, CS(T, alpha), CP(T, A), lda, CP(T, B), ldb, beta, MP(T, C), ldc); }
+CPLX_L3X(c, cfloat, float)
+CPLX_L3X(z, cdouble, double)
+}

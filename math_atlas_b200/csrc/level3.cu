@@ -344,6 +344,68 @@ void trsm(int side, int uplo, int trans, int diag, int M, int N, T alpha, const 
   trsm_rec<T>(side, uplo, trans, diag, M, N, alpha, A, lda, B, ldb, abort_flag);
 }
 
+// ------------------------------------------------------------------------------------- SYMM / HEMM / SYR2K / HER2K
+// SURVEY section 8(f) item 1 (reference Clint/l3micro.base:1-1100, 4803-7585).  The reference copies
+// the symmetric operand into full access-major blocks (sy{L,R}{L,U}2ipBlk, l3micro.base:5605-6170)
+// and runs its GEMM loops; here the triangle is expanded once into a dense workspace matrix
+// (O(n^2) against the O(n^2 m) multiply) and the fast GEMM kernels do the rest.
+template <typename T>
+__global__ void symmetrize_kernel(int upper, int herm, int n, const T* __restrict__ A, size_t lda, T* __restrict__ W, size_t ldw) {
+  using S = ST<T>;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x, j = blockIdx.y * blockDim.y + threadIdx.y;
+  if (i >= n || j >= n) return;
+  const bool stored = upper ? (i <= j) : (i >= j);
+  T v = stored ? A[(size_t)i + (size_t)j * lda] : A[(size_t)j + (size_t)i * lda];
+  if constexpr (S::cplx) {
+    if (herm) { if (!stored) v = S::conj(v); if (i == j) v.y = 0; }
+  }
+  W[(size_t)i + (size_t)j * ldw] = v;
+}
+
+template <typename T>
+void symm(int side, int uplo, int herm, int M, int N, T alpha, const T* A, size_t lda, const T* B, size_t ldb, T beta, T* C, size_t ldc) {
+  using S = ST<T>;
+  if (M <= 0 || N <= 0) return;
+  if (S::is_zero(alpha)) { gemm_flags<T>(0, 0, 0, 0, M, N, 0, S::zero(), C, ldc, C, ldc, beta, C, ldc, C_FULL, 0, nullptr); return; }
+  const int nA = (side == Left) ? M : N;
+  const size_t ldw = ((size_t)nA + 15) & ~(size_t)15;
+  T* W = static_cast<T*>(workspace(sizeof(T) * ldw * (size_t)nA, 4));
+  dim3 blk(32, 8), grd((nA + 31) / 32, (nA + 7) / 8);
+  symmetrize_kernel<T><<<grd, blk, 0, current_stream()>>>(uplo == Upper, herm, nA, A, lda, W, ldw);
+  count_launch();
+  if (side == Left) gemm<T>(NoTrans, NoTrans, M, N, M, alpha, W, ldw, B, ldb, beta, C, ldc);
+  else gemm<T>(NoTrans, NoTrans, M, N, N, alpha, B, ldb, W, ldw, beta, C, ldc);
+}
+
+// C(uplo) <- alpha*op(A)*op(B)^T + alpha*op(B)*op(A)^T + beta*C
+template <typename T>
+void syr2k(int uplo, int trans, int N, int K, T alpha, const T* A, size_t lda, const T* B, size_t ldb, T beta, T* C, size_t ldc) {
+  using S = ST<T>;
+  const int cm = (uplo == Upper) ? C_UPPER : C_LOWER;
+  const int t = is_tr(trans);
+  gemm_flags<T>(t, 0, !t, 0, N, N, K, alpha, A, lda, B, ldb, beta, C, ldc, cm, 0, nullptr);
+  if (!S::is_zero(alpha) && K > 0) gemm_flags<T>(t, 0, !t, 0, N, N, K, alpha, B, ldb, A, lda, S::one(), C, ldc, cm, 0, nullptr);
+}
+
+// C(uplo) <- alpha*op(A)*op(B)^H + conj(alpha)*op(B)*op(A)^H + beta*C, beta real, Im(diag) = 0
+template <typename T>
+void her2k(int uplo, int trans, int N, int K, T alpha, const T* A, size_t lda, const T* B, size_t ldb, typename ST<T>::real beta,
+           T* C, size_t ldc) {
+  using S = ST<T>;
+  const int cm = (uplo == Upper) ? C_UPPER : C_LOWER;
+  const int t = is_tr(trans);   // NoTrans: A*B^H ; ConjTrans: A^H*B
+  gemm_flags<T>(t, t, !t, !t, N, N, K, alpha, A, lda, B, ldb, S::from_real(beta), C, ldc, cm, 1, nullptr);
+  if (!S::is_zero(alpha) && K > 0)
+    gemm_flags<T>(t, t, !t, !t, N, N, K, S::conj(alpha), B, ldb, A, lda, S::one(), C, ldc, cm, 1, nullptr);
+}
+
+#define AB_INST2(T)                                                                                                    \
+  template void symm<T>(int, int, int, int, int, T, const T*, size_t, const T*, size_t, T, T*, size_t);              \
+  template void syr2k<T>(int, int, int, int, T, const T*, size_t, const T*, size_t, T, T*, size_t);
+AB_INST2(float) AB_INST2(double) AB_INST2(float2) AB_INST2(double2)
+template void her2k<float2>(int, int, int, int, float2, const float2*, size_t, const float2*, size_t, float, float2*, size_t);
+template void her2k<double2>(int, int, int, int, double2, const double2*, size_t, const double2*, size_t, double, double2*, size_t);
+
 #define AB_INST(T)                                                                                                     \
   template void gemm<T>(int, int, int, int, int, T, const T*, size_t, const T*, size_t, T, T*, size_t, const int*);   \
   template void syrk<T>(int, int, int, int, T, const T*, size_t, T, T*, size_t, const int*);                          \
