@@ -60,7 +60,11 @@ def _declare(L):
         getattr(L, f"ATL_{p}syrk").argtypes = [I, I, Z, Z, S, VP, Z, S, VP, Z]
         getattr(L, f"ATL_{p}trsm").argtypes = [I, I, I, I, Z, Z, S, VP, Z, VP, Z]
         getattr(L, f"ATL_{p}trmm").argtypes = [I, I, I, I, Z, Z, S, VP, Z, VP, Z]
+        getattr(L, f"cblas_{p}symm").argtypes = [I, I, I, I, I, S, VP, I, VP, I, S, VP, I]
+        getattr(L, f"cblas_{p}syr2k").argtypes = [I, I, I, I, I, S, VP, I, VP, I, S, VP, I]
         if _CPLX[p]:
+            getattr(L, f"cblas_{p}hemm").argtypes = [I, I, I, I, I, S, VP, I, VP, I, S, VP, I]
+            getattr(L, f"cblas_{p}her2k").argtypes = [I, I, I, I, I, S, VP, I, VP, I, R, VP, I]
             getattr(L, f"cblas_{p}herk").argtypes = [I, I, I, I, I, R, VP, I, R, VP, I]
             getattr(L, f"ATL_{p}herk").argtypes = [I, I, Z, Z, R, VP, Z, R, VP, Z]
         for nm in (f"clapack_{p}getrf", f"ATL_{p}getrf"):
@@ -114,6 +118,26 @@ def cblas_syrk(p, Order, Uplo, Trans, N, K, alpha, A, lda, beta, Cm, ldc):
 
 def cblas_herk(p, Order, Uplo, Trans, N, K, alpha, A, lda, beta, Cm, ldc):
     getattr(lib(), f"cblas_{p}herk")(Order, Uplo, Trans, N, K, float(alpha), ptr(A), lda, float(beta), ptr(Cm), ldc)
+
+
+def cblas_symm(p, Order, Side, Uplo, M, N, alpha, A, lda, B, ldb, beta, Cm, ldc):
+    a, b = _Scalar(p, alpha), _Scalar(p, beta)
+    getattr(lib(), f"cblas_{p}symm")(Order, Side, Uplo, M, N, a.arg, ptr(A), lda, ptr(B), ldb, b.arg, ptr(Cm), ldc)
+
+
+def cblas_hemm(p, Order, Side, Uplo, M, N, alpha, A, lda, B, ldb, beta, Cm, ldc):
+    a, b = _Scalar(p, alpha), _Scalar(p, beta)
+    getattr(lib(), f"cblas_{p}hemm")(Order, Side, Uplo, M, N, a.arg, ptr(A), lda, ptr(B), ldb, b.arg, ptr(Cm), ldc)
+
+
+def cblas_syr2k(p, Order, Uplo, Trans, N, K, alpha, A, lda, B, ldb, beta, Cm, ldc):
+    a, b = _Scalar(p, alpha), _Scalar(p, beta)
+    getattr(lib(), f"cblas_{p}syr2k")(Order, Uplo, Trans, N, K, a.arg, ptr(A), lda, ptr(B), ldb, b.arg, ptr(Cm), ldc)
+
+
+def cblas_her2k(p, Order, Uplo, Trans, N, K, alpha, A, lda, B, ldb, beta, Cm, ldc):
+    a = _Scalar(p, alpha)
+    getattr(lib(), f"cblas_{p}her2k")(Order, Uplo, Trans, N, K, a.arg, ptr(A), lda, ptr(B), ldb, float(beta), ptr(Cm), ldc)
 
 
 def cblas_trsm(p, Order, Side, Uplo, TA, Diag, M, N, alpha, A, lda, B, ldb):

@@ -305,9 +305,10 @@ void launch(const CUtensorMap& ta, const CUtensorMap& tb, double* C, size_t ldc,
   int grid = std::min(tiles_m * tiles_n, gemm_cta_cap());
   SmMask mask = {{0, 0, 0, 0}};
   int* counter = nullptr;
-  if (g_reserved_on && tiles_m * tiles_n > 16) {
-    // one CTA per SM, the ones on reserved SMs leave, the rest share the tiles through a counter
-    mask = g_reserved;
+  if ((g_reserved_on || cmode != C_FULL) && tiles_m * tiles_n > 2 * gemm_cta_cap()) {
+    // one CTA per SM; the ones on reserved SMs leave, the rest share the tiles through a counter
+    // (also used for SYRK: half of the tiles are skipped, a static stride would be unbalanced)
+    if (g_reserved_on) mask = g_reserved;
     grid = gemm_cta_cap();
     if (!g_counters) AB_CUDA_CHECK(cudaMalloc(&g_counters, NCOUNTERS * sizeof(int)));
     counter = g_counters + (g_counter_next++ % NCOUNTERS);

@@ -122,6 +122,18 @@ class Oracle(_Base):
         r = _CREAL[pre]
         getattr(self.lib, f"orc_{pre}herk")(uplo, trans, N, K, r(alpha), _p(a), self._ld(a), r(beta), _p(c), self._ld(c))
 
+    def symm(self, pre, side, uplo, M, N, alpha, a, b, beta, c, herm=False):
+        ka, pa = self._sp(pre, alpha); kb, pb = self._sp(pre, beta)
+        getattr(self.lib, f"orc_{pre}symm")(side, uplo, 1 if herm else 0, M, N, pa, _p(a), self._ld(a), _p(b), self._ld(b), pb, _p(c), self._ld(c))
+
+    def syr2k(self, pre, uplo, trans, N, K, alpha, a, b, beta, c):
+        ka, pa = self._sp(pre, alpha); kb, pb = self._sp(pre, beta)
+        getattr(self.lib, f"orc_{pre}syr2k")(uplo, trans, N, K, pa, _p(a), self._ld(a), _p(b), self._ld(b), pb, _p(c), self._ld(c))
+
+    def her2k(self, pre, uplo, trans, N, K, alpha, a, b, beta, c):
+        ka, pa = self._sp(pre, alpha)
+        getattr(self.lib, f"orc_{pre}her2k")(uplo, trans, N, K, pa, _p(a), self._ld(a), _p(b), self._ld(b), _CREAL[pre](beta), _p(c), self._ld(c))
+
     def trsm(self, pre, side, uplo, trans, diag, M, N, alpha, a, b):
         ka, pa = self._sp(pre, alpha)
         getattr(self.lib, f"orc_{pre}trsm")(side, uplo, trans, diag, M, N, pa, _p(a), self._ld(a), _p(b), self._ld(b))
@@ -199,6 +211,19 @@ class Ref(_Base):
     def herk(self, pre, uplo, trans, N, K, alpha, a, beta, c):
         r = _CREAL[pre]
         getattr(self.lib, f"ATL_{pre}refherk")(uplo, trans, N, K, r(alpha), _p(a), self._ld(a), r(beta), _p(c), self._ld(c))
+
+    def symm(self, pre, side, uplo, M, N, alpha, a, b, beta, c, herm=False):
+        ka, pa = _sc(pre, alpha); kb, pb = _sc(pre, beta)
+        nm = "refhemm" if herm else "refsymm"
+        getattr(self.lib, f"ATL_{pre}{nm}")(side, uplo, M, N, pa, _p(a), self._ld(a), _p(b), self._ld(b), pb, _p(c), self._ld(c))
+
+    def syr2k(self, pre, uplo, trans, N, K, alpha, a, b, beta, c):
+        ka, pa = _sc(pre, alpha); kb, pb = _sc(pre, beta)
+        getattr(self.lib, f"ATL_{pre}refsyr2k")(uplo, trans, N, K, pa, _p(a), self._ld(a), _p(b), self._ld(b), pb, _p(c), self._ld(c))
+
+    def her2k(self, pre, uplo, trans, N, K, alpha, a, b, beta, c):
+        ka, pa = _sc(pre, alpha)
+        getattr(self.lib, f"ATL_{pre}refher2k")(uplo, trans, N, K, pa, _p(a), self._ld(a), _p(b), self._ld(b), _CREAL[pre](beta), _p(c), self._ld(c))
 
     def trsm(self, pre, side, uplo, trans, diag, M, N, alpha, a, b):
         ka, pa = _sc(pre, alpha)

@@ -347,6 +347,69 @@ void FN(trsm)(int side, int uplo, int trans, int diag, int M, int N, const S* pa
   }
 }
 
+/* ------------------------------------------------------------------ symm / hemm / syr2k / her2k
+   (reference Antoine/atlrefblas.base ATL_Xrefsymm*, refhemm*, refsyr2k*, refher2k*) */
+static inline S FN(symel)(const S* A, int lda, int uplo, int herm, int i, int j) { /* full matrix element from one triangle */
+  const int st = (uplo == 121) ? (i <= j) : (i >= j);
+  S v = st ? EL(A, lda, i, j) : EL(A, lda, j, i);
+#ifdef ORC_CPLX
+  if (herm) { if (!st) v = S_CONJ(v); if (i == j) v.im = 0; }
+#endif
+  return v;
+}
+void FN(symm)(int side, int uplo, int herm, int M, int N, const S* palpha, const S* A, int lda, const S* B, int ldb,
+              const S* pbeta, S* C, int ldc) {
+  const S alpha = *palpha, beta = *pbeta;
+  for (int j = 0; j < N; j++)
+    for (int i = 0; i < M; i++) {
+      S t = S_ZERO;
+      if (!S_ISZERO(alpha)) {
+        if (side == 141) for (int l = 0; l < M; l++) t = S_ADD(t, S_MUL(FN(symel)(A, lda, uplo, herm, i, l), EL(B, ldb, l, j)));
+        else             for (int l = 0; l < N; l++) t = S_ADD(t, S_MUL(EL(B, ldb, i, l), FN(symel)(A, lda, uplo, herm, l, j)));
+      }
+      S c = S_ISZERO(beta) ? S_ZERO : S_MUL(beta, EL(C, ldc, i, j));
+      EL(C, ldc, i, j) = S_ADD(c, S_MUL(alpha, t));
+    }
+}
+void FN(syr2k)(int uplo, int trans, int N, int K, const S* palpha, const S* A, int lda, const S* B, int ldb, const S* pbeta, S* C, int ldc) {
+  const S alpha = *palpha, beta = *pbeta;
+  for (int j = 0; j < N; j++) {
+    int i0 = (uplo == 121) ? 0 : j, i1 = (uplo == 121) ? j + 1 : N;
+    for (int i = i0; i < i1; i++) {
+      S t = S_ZERO;
+      if (!S_ISZERO(alpha))
+        for (int l = 0; l < K; l++) {
+          S ai = (trans == 111) ? EL(A, lda, i, l) : EL(A, lda, l, i), aj = (trans == 111) ? EL(A, lda, j, l) : EL(A, lda, l, j);
+          S bi = (trans == 111) ? EL(B, ldb, i, l) : EL(B, ldb, l, i), bj = (trans == 111) ? EL(B, ldb, j, l) : EL(B, ldb, l, j);
+          t = S_ADD(t, S_ADD(S_MUL(ai, bj), S_MUL(bi, aj)));
+        }
+      S c = S_ISZERO(beta) ? S_ZERO : S_MUL(beta, EL(C, ldc, i, j));
+      EL(C, ldc, i, j) = S_ADD(c, S_MUL(alpha, t));
+    }
+  }
+}
+#ifdef ORC_CPLX
+void FN(her2k)(int uplo, int trans, int N, int K, const S* palpha, const S* A, int lda, const S* B, int ldb, R beta, S* C, int ldc) {
+  const S alpha = *palpha;
+  for (int j = 0; j < N; j++) {
+    int i0 = (uplo == 121) ? 0 : j, i1 = (uplo == 121) ? j + 1 : N;
+    for (int i = i0; i < i1; i++) {
+      S t1 = S_ZERO, t2 = S_ZERO;   /* t1 = sum op(A)(i,l) conj(op(B)(j,l)), t2 = sum op(B)(i,l) conj(op(A)(j,l)) */
+      if (!S_ISZERO(alpha))
+        for (int l = 0; l < K; l++) {
+          S ai = (trans == 111) ? EL(A, lda, i, l) : S_CONJ(EL(A, lda, l, i)), aj = (trans == 111) ? EL(A, lda, j, l) : S_CONJ(EL(A, lda, l, j));
+          S bi = (trans == 111) ? EL(B, ldb, i, l) : S_CONJ(EL(B, ldb, l, i)), bj = (trans == 111) ? EL(B, ldb, j, l) : S_CONJ(EL(B, ldb, l, j));
+          t1 = S_ADD(t1, S_MUL(ai, S_CONJ(bj))); t2 = S_ADD(t2, S_MUL(bi, S_CONJ(aj)));
+        }
+      S c = (beta == 0) ? S_ZERO : MK(beta * EL(C, ldc, i, j).re, beta * EL(C, ldc, i, j).im);
+      c = S_ADD(c, S_ADD(S_MUL(alpha, t1), S_MUL(S_CONJ(alpha), t2)));
+      if (i == j) c.im = 0;
+      EL(C, ldc, i, j) = c;
+    }
+  }
+}
+#endif
+
 /* ------------------------------------------------------------------ LU */
 static int FN(iamax)(int n, const S* x) { /* first index of strictly larger |x| (|re|+|im| for complex) */
   int im = 0; R mx = -1;
