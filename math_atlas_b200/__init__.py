@@ -72,6 +72,10 @@ def _declare(L):
         for nm in (f"clapack_{p}potrf", f"ATL_{p}potrf"):
             getattr(L, nm).argtypes = [I, I, I, VP, I]; getattr(L, nm).restype = I
         getattr(L, f"ATL_{p}laswp").argtypes = [I, VP, I, I, I, VP, I]
+        for nm, at in (("gesv", [I, I, I, VP, I, VP, VP, I]), ("getrs", [I, I, I, I, VP, I, VP, VP, I]), ("getri", [I, I, VP, I, VP]),
+                       ("posv", [I, I, I, I, VP, I, VP, I]), ("potrs", [I, I, I, I, VP, I, VP, I]), ("potri", [I, I, I, VP, I]),
+                       ("lauum", [I, I, I, VP, I]), ("trtri", [I, I, I, I, VP, I])):
+            getattr(L, f"clapack_{p}{nm}").argtypes = at; getattr(L, f"clapack_{p}{nm}").restype = I
         for nm in ("gemm", "syrk", "trsm", "trmm", "getrf", "potrf") + (("herk",) if _CPLX[p] else ()):
             getattr(L, f"{p}{nm}_").restype = None
     L.atlb200_launch_count.restype = C.c_longlong
@@ -163,6 +167,38 @@ def clapack_potrf(p, Order, Uplo, N, A, lda):
     return getattr(lib(), f"clapack_{p}potrf")(Order, Uplo, N, ptr(A), lda)
 
 
+def clapack_gesv(p, Order, N, NRHS, A, lda, ipiv, B, ldb):
+    return getattr(lib(), f"clapack_{p}gesv")(Order, N, NRHS, ptr(A), lda, ptr(ipiv), ptr(B), ldb)
+
+
+def clapack_getrs(p, Order, Trans, N, NRHS, A, lda, ipiv, B, ldb):
+    return getattr(lib(), f"clapack_{p}getrs")(Order, Trans, N, NRHS, ptr(A), lda, ptr(ipiv), ptr(B), ldb)
+
+
+def clapack_getri(p, Order, N, A, lda, ipiv):
+    return getattr(lib(), f"clapack_{p}getri")(Order, N, ptr(A), lda, ptr(ipiv))
+
+
+def clapack_posv(p, Order, Uplo, N, NRHS, A, lda, B, ldb):
+    return getattr(lib(), f"clapack_{p}posv")(Order, Uplo, N, NRHS, ptr(A), lda, ptr(B), ldb)
+
+
+def clapack_potrs(p, Order, Uplo, N, NRHS, A, lda, B, ldb):
+    return getattr(lib(), f"clapack_{p}potrs")(Order, Uplo, N, NRHS, ptr(A), lda, ptr(B), ldb)
+
+
+def clapack_potri(p, Order, Uplo, N, A, lda):
+    return getattr(lib(), f"clapack_{p}potri")(Order, Uplo, N, ptr(A), lda)
+
+
+def clapack_lauum(p, Order, Uplo, N, A, lda):
+    return getattr(lib(), f"clapack_{p}lauum")(Order, Uplo, N, ptr(A), lda)
+
+
+def clapack_trtri(p, Order, Uplo, Diag, N, A, lda):
+    return getattr(lib(), f"clapack_{p}trtri")(Order, Uplo, Diag, N, ptr(A), lda)
+
+
 def ATL_laswp(p, N, A, lda, K1, K2, piv, inci):
     getattr(lib(), f"ATL_{p}laswp")(N, ptr(A), lda, K1, K2, ptr(piv), inci)
 
@@ -182,6 +218,8 @@ for _p in "sdcz":
     globals()[f"cblas_{_p}trmm"] = _bind(f"cblas_{_p}trmm", cblas_trmm, _p)
     globals()[f"clapack_{_p}getrf"] = _bind(f"clapack_{_p}getrf", clapack_getrf, _p)
     globals()[f"clapack_{_p}potrf"] = _bind(f"clapack_{_p}potrf", clapack_potrf, _p)
+    for _nm in ("gesv", "getrs", "getri", "posv", "potrs", "potri", "lauum", "trtri"):
+        globals()[f"clapack_{_p}{_nm}"] = _bind(f"clapack_{_p}{_nm}", globals()[f"clapack_{_nm}"], _p)
     if _CPLX[_p]:
         globals()[f"cblas_{_p}herk"] = _bind(f"cblas_{_p}herk", cblas_herk, _p)
 

@@ -62,6 +62,28 @@ void getrf(int M, int N, T* A, size_t lda, int* d_ipiv, int* d_info);
 template <typename T>
 void potrf(int uplo, int N, T* A, size_t lda, int* d_info);
 
+// ---- solve / inverse layer (lapack_inv.cu) ---------------------------------
+// B <- solution of op(A) X = B from getrf's factors; order/trans as ATL_getrs (atlas-lp.base:1631)
+template <typename T>
+void getrs(int order, int trans, int N, int NRHS, const T* A, size_t lda, const int* d_ipiv, T* B, size_t ldb);
+// B <- solution of A X = B from potrf's factor (ATL_potrs, atlas-lp.base:969)
+template <typename T>
+void potrs(int order, int uplo, int N, int NRHS, const T* A, size_t lda, T* B, size_t ldb);
+// *d_info <- 1-based index of the first zero diagonal element of a NonUnit triangle (ATL_trtri, :2341)
+template <typename T>
+void trtri_check(int diag, int N, const T* A, size_t lda, int* d_info);
+// column-major triangular inverse in place (ATL_trtriCL/CU, :1902-2199); call trtri_check first
+template <typename T>
+void trtri(int uplo, int diag, int N, T* A, size_t lda);
+// column-major U*U^H (Upper) or L^H*L (Lower) in place (ATL_lauumCU/CL, :221-311)
+template <typename T>
+void lauum(int uplo, int N, T* A, size_t lda);
+// the part of ATL_getriC (:135-201) after trtri(Upper): inv(A)*L = inv(U), then column interchanges
+template <typename T>
+void getri_finish(int N, T* A, size_t lda, const int* d_ipiv);
+template <typename T>
+void conj_inplace(int M, int N, T* B, size_t ldb);
+
 // Grow-only per-thread device workspace (freed by free_workspace()).
 void* workspace(size_t bytes, int slot = 0);
 void free_workspace();

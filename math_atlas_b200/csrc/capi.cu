@@ -827,3 +827,269 @@ REAL_L3X(d, double)
 CPLX_L3X(c, cfloat, float)
 CPLX_L3X(z, cdouble, double)
 }
+
+// ------------------------------------------------------------------------------------- solve / inverse layer
+// getrs/potrs/gesv/posv/trtri/lauum/getri/potri (reference
+// Clint/atlas-lp.base:16-331, 969-1052, 1631-2381; wrappers Clint/atlas-clp.base:62-454).
+// A RowMajor matrix is the column-major transpose in the same memory: Uplo flips, getri is unchanged.
+static int read_info(DevInts& info) {
+  int h = 0;
+  AB_CUDA_CHECK(cudaMemcpyAsync(&h, info.d, sizeof(int), cudaMemcpyDeviceToHost, current_stream()));
+  AB_CUDA_CHECK(cudaStreamSynchronize(current_stream()));
+  return h;
+}
+static inline int flip_uplo(int order, int uplo) { return order == ColMajor ? uplo : (uplo == Upper ? Lower : Upper); }
+
+template <typename T>
+static void atl_getrs(int order, int trans, int N, int NRHS, const T* A, int lda, const int* ipiv, T* B, int ldb) {
+  if (N <= 0 || NRHS <= 0) return;
+  Operand<T> a(A, N, N, (size_t)lda, true, false), b(B, N, NRHS, (size_t)ldb, true, true);
+  DevInts piv(const_cast<int*>(ipiv), N, true);
+  getrs<T>(order, trans, N, NRHS, a.d, a.ld, piv.d, b.d, b.ld);
+  a.finish(); b.finish(); piv.finish(false);
+  sync_stream();
+}
+template <typename T>
+static void atl_potrs(int order, int uplo, int N, int NRHS, const T* A, int lda, T* B, int ldb) {
+  if (N <= 0 || NRHS <= 0) return;
+  Operand<T> a(A, N, N, (size_t)lda, true, false), b(B, N, NRHS, (size_t)ldb, true, true);
+  potrs<T>(order, uplo, N, NRHS, a.d, a.ld, b.d, b.ld);
+  a.finish(); b.finish();
+  sync_stream();
+}
+template <typename T>
+static int atl_gesv(int order, int N, int NRHS, T* A, int lda, int* ipiv, T* B, int ldb) {
+  if (N <= 0) return 0;
+  Operand<T> a(A, N, N, (size_t)lda, true, true), b(B, N, NRHS, (size_t)ldb, true, true);
+  DevInts piv(ipiv, N, false);
+  int h_info = 0;
+  DevInts info(&h_info, 1, false);
+  getrf<T>(N, N, a.d, a.ld, piv.d, info.d);
+  const int ierr = read_info(info);
+  if (!ierr) getrs<T>(order, NoTrans, N, NRHS, a.d, a.ld, piv.d, b.d, b.ld);
+  a.finish(); b.finish(); piv.finish(true); info.finish(false);
+  sync_stream();
+  return ierr;
+}
+template <typename T>
+static int atl_posv(int order, int uplo, int N, int NRHS, T* A, int lda, T* B, int ldb) {
+  if (N <= 0) return 0;
+  Operand<T> a(A, N, N, (size_t)lda, true, true), b(B, N, NRHS, (size_t)ldb, true, true);
+  int h_info = 0;
+  DevInts info(&h_info, 1, false);
+  potrf<T>(flip_uplo(order, uplo), N, a.d, a.ld, info.d);
+  const int ierr = read_info(info);
+  if (!ierr) potrs<T>(order, uplo, N, NRHS, a.d, a.ld, b.d, b.ld);
+  a.finish(); b.finish(); info.finish(false);
+  sync_stream();
+  return ierr;
+}
+// what = 0: trtri, 1: lauum, 2: potri (= trtri NonUnit + lauum)
+template <typename T>
+static int atl_triop(int what, int order, int uplo, int diag, int N, T* A, int lda) {
+  if (N <= 0) return 0;
+  const int ul = flip_uplo(order, uplo);
+  Operand<T> a(A, N, N, (size_t)lda, true, true);
+  int ierr = 0;
+  if (what != 1) {
+    int h_info = 0;
+    DevInts info(&h_info, 1, false);
+    trtri_check<T>(diag, N, a.d, a.ld, info.d);     // singular: return before touching A (atlas-lp.base:2353-2363)
+    ierr = read_info(info);
+    info.finish(false);
+    if (!ierr) trtri<T>(ul, diag, N, a.d, a.ld);
+  }
+  if (what != 0 && !ierr) lauum<T>(ul, N, a.d, a.ld);
+  a.finish();
+  sync_stream();
+  return ierr;
+}
+template <typename T>
+static int atl_getri(int order, int N, T* A, int lda, const int* ipiv) {
+  (void)order;   // inverse of the transpose = transpose of the inverse: same memory operations
+  if (N <= 0) return 0;
+  Operand<T> a(A, N, N, (size_t)lda, true, true);
+  DevInts piv(const_cast<int*>(ipiv), N, true);
+  int h_info = 0;
+  DevInts info(&h_info, 1, false);
+  trtri_check<T>(NonUnit, N, a.d, a.ld, info.d);
+  const int ierr = read_info(info);
+  if (!ierr) {
+    trtri<T>(Upper, NonUnit, N, a.d, a.ld);
+    getri_finish<T>(N, a.d, a.ld, piv.d);
+  }
+  a.finish(); piv.finish(false); info.finish(false);
+  sync_stream();
+  return ierr;
+}
+
+// ---- clapack_* argument checks (numbering and texts of atlas-clp.base)
+static int cl_order(const char* rout, int Order) {
+  if (Order != RowMajor && Order != ColMajor) { cblas_xerbla(1, rout, "Order must be %d or %d, but is set to %d\n", RowMajor, ColMajor, Order); return -1; }
+  return 0;
+}
+static int cl_uplo(const char* rout, int Uplo) {
+  if (Uplo != Upper && Uplo != Lower) { cblas_xerbla(2, rout, "Uplo must be %d or %d, but is set to %d\n", Upper, Lower, Uplo); return -2; }
+  return 0;
+}
+static int cl_nonneg(const char* rout, int pos, const char* name, int v) {
+  if (v < 0) { cblas_xerbla(pos, rout, "%s cannot be less than zero 0,; is set to %d.\n", name, v); return -pos; }
+  return 0;
+}
+static int cl_ld(const char* rout, int pos, const char* name, int ld, int N) {
+  if (ld < N || ld < 1) { cblas_xerbla(pos, rout, "%s must be >= MAX(N,1): %s=%d N=%d\n", name, name, ld, N); return -pos; }
+  return 0;
+}
+#define CL_CHECK(expr) do { const int e_ = (expr); if (e_) ierr = e_; } while (0)
+
+template <typename T>
+static int cl_gesv(const char* rout, int Order, int N, int NRHS, T* A, int lda, int* ipiv, T* B, int ldb) {
+  int ierr = 0;
+  CL_CHECK(cl_order(rout, Order)); CL_CHECK(cl_nonneg(rout, 2, "N", N)); CL_CHECK(cl_nonneg(rout, 3, "NRHS", NRHS));
+  CL_CHECK(cl_ld(rout, 5, "lda", lda, N)); CL_CHECK(cl_ld(rout, 8, "ldb", ldb, N));
+  return ierr ? ierr : atl_gesv<T>(Order, N, NRHS, A, lda, ipiv, B, ldb);
+}
+template <typename T>
+static int cl_getrs(const char* rout, int Order, int Trans, int N, int NRHS, const T* A, int lda, const int* ipiv, T* B, int ldb) {
+  int ierr = 0;
+  CL_CHECK(cl_order(rout, Order));
+  if (Trans != NoTrans && Trans != TransT && Trans != ConjTrans) {
+    ierr = -2; cblas_xerbla(2, rout, "Trans must be %d, %d, or %d, but is set to %d\n", NoTrans, TransT, ConjTrans, Trans);
+  }
+  CL_CHECK(cl_nonneg(rout, 3, "N", N)); CL_CHECK(cl_nonneg(rout, 4, "NRHS", NRHS));
+  CL_CHECK(cl_ld(rout, 6, "lda", lda, N)); CL_CHECK(cl_ld(rout, 9, "ldb", ldb, N));
+  if (!ierr) atl_getrs<T>(Order, Trans, N, NRHS, A, lda, ipiv, B, ldb);
+  return ierr;
+}
+template <typename T>
+static int cl_posv(const char* rout, bool factor, int Order, int Uplo, int N, int NRHS, T* A, int lda, T* B, int ldb) {
+  int ierr = 0;
+  CL_CHECK(cl_order(rout, Order)); CL_CHECK(cl_uplo(rout, Uplo)); CL_CHECK(cl_nonneg(rout, 3, "N", N));
+  CL_CHECK(cl_nonneg(rout, 4, "NRHS", NRHS)); CL_CHECK(cl_ld(rout, 6, "lda", lda, N)); CL_CHECK(cl_ld(rout, 8, "ldb", ldb, N));
+  if (ierr) return ierr;
+  if (factor) return atl_posv<T>(Order, Uplo, N, NRHS, A, lda, B, ldb);
+  atl_potrs<T>(Order, Uplo, N, NRHS, A, lda, B, ldb);
+  return 0;
+}
+template <typename T>
+static int cl_triop(const char* rout, int what, int Order, int Uplo, int Diag, int N, T* A, int lda) {
+  int ierr = 0;   // (the reference's clapack_Xtrtri leaves ierr uninitialised, atlas-clp.base:417; 0 is what it means)
+  CL_CHECK(cl_order(rout, Order)); CL_CHECK(cl_uplo(rout, Uplo));
+  if (what == 0) {
+    if (Diag != Unit && Diag != NonUnit) { ierr = -3; cblas_xerbla(3, rout, "Diag must be %d or %d, but is set to %d\n", NonUnit, Unit, Diag); }
+    CL_CHECK(cl_nonneg(rout, 4, "N", N)); CL_CHECK(cl_ld(rout, 6, "lda", lda, N));
+  } else {
+    CL_CHECK(cl_nonneg(rout, 3, "N", N)); CL_CHECK(cl_ld(rout, 5, "lda", lda, N));
+  }
+  return ierr ? ierr : atl_triop<T>(what, Order, Uplo, Diag, N, A, lda);
+}
+
+// ---- F77 front ends (netlib LAPACK argument numbering; pivots 1-based on the Fortran side)
+template <typename T>
+static void f_getrs(const char* name, bool factor, const char* tr, const int* n, const int* nrhs, T* A, const int* lda, int* ipiv, T* B,
+                    const int* ldb, int* info) {
+  const int TR = factor ? NoTrans : f_trans(tr);
+  *info = 0;
+  if (factor) {
+    if (*n < 0) *info = -1; else if (*nrhs < 0) *info = -2; else if (*lda < imax(1, *n)) *info = -4; else if (*ldb < imax(1, *n)) *info = -7;
+  } else {
+    if (TR < 0) *info = -1; else if (*n < 0) *info = -2; else if (*nrhs < 0) *info = -3; else if (*lda < imax(1, *n)) *info = -5;
+    else if (*ldb < imax(1, *n)) *info = -8;
+  }
+  if (*info) { int p = -*info; xerbla_(name, &p, strlen(name)); return; }
+  if (*n == 0) return;
+  if (is_device_ptr(ipiv)) { fprintf(stderr, "atlas_b200: %s needs a host ipiv array\n", name); abort(); }
+  if (factor) {
+    *info = atl_gesv<T>(ColMajor, *n, *nrhs, A, *lda, ipiv, B, *ldb);
+    for (int i = 0; i < *n; i++) ipiv[i]++;
+  } else {
+    std::unique_ptr<int[]> p0(new int[*n]);
+    for (int i = 0; i < *n; i++) p0[i] = ipiv[i] - 1;
+    atl_getrs<T>(ColMajor, TR, *n, *nrhs, A, *lda, p0.get(), B, *ldb);
+  }
+}
+template <typename T>
+static void f_potrs(const char* name, bool factor, const char* ul, const int* n, const int* nrhs, T* A, const int* lda, T* B, const int* ldb,
+                    int* info) {
+  const int UL = f_uplo(ul);
+  *info = 0;
+  if (UL < 0) *info = -1; else if (*n < 0) *info = -2; else if (*nrhs < 0) *info = -3; else if (*lda < imax(1, *n)) *info = -5;
+  else if (*ldb < imax(1, *n)) *info = -7;
+  if (*info) { int p = -*info; xerbla_(name, &p, strlen(name)); return; }
+  if (factor) *info = atl_posv<T>(ColMajor, UL, *n, *nrhs, A, *lda, B, *ldb);
+  else atl_potrs<T>(ColMajor, UL, *n, *nrhs, A, *lda, B, *ldb);
+}
+template <typename T>
+static void f_triop(const char* name, int what, const char* ul, const char* dg, const int* n, T* A, const int* lda, int* info) {
+  const int UL = f_uplo(ul), DG = what == 0 ? f_diag(dg) : NonUnit;
+  *info = 0;
+  if (UL < 0) *info = -1;
+  else if (what == 0) { if (DG < 0) *info = -2; else if (*n < 0) *info = -3; else if (*lda < imax(1, *n)) *info = -5; }
+  else { if (*n < 0) *info = -2; else if (*lda < imax(1, *n)) *info = -4; }
+  if (*info) { int p = -*info; xerbla_(name, &p, strlen(name)); return; }
+  *info = atl_triop<T>(what, ColMajor, UL, DG, *n, A, *lda);
+}
+template <typename T>
+static void f_getri(const char* name, const int* n, T* A, const int* lda, const int* ipiv, T* work, const int* lwork, int* info) {
+  *info = 0;
+  if (*n < 0) *info = -1; else if (*lda < imax(1, *n)) *info = -3; else if (*lwork < imax(1, *n) && *lwork != -1) *info = -6;
+  if (*info) { int p = -*info; xerbla_(name, &p, strlen(name)); return; }
+  if (work) { memset(work, 0, sizeof(T)); *reinterpret_cast<typename ST<T>::real*>(work) = (typename ST<T>::real)imax(1, *n * 64); }
+  if (*lwork == -1 || *n == 0) return;   // workspace query: the device routine brings its own
+  std::unique_ptr<int[]> p0(new int[*n]);
+  for (int i = 0; i < *n; i++) p0[i] = ipiv[i] - 1;
+  *info = atl_getri<T>(ColMajor, *n, A, *lda, p0.get());
+}
+
+extern "C" {
+#define SOLVE_API(P, T, AT, RT, UP)                                                                                            \
+  int clapack_##P##gesv(int Order, int N, int NRHS, AT* A, int lda, int* ipiv, AT* B, int ldb) {                               \
+    return cl_gesv<T>("clapack_" #P "gesv", Order, N, NRHS, MP(T, A), lda, ipiv, MP(T, B), ldb); }                             \
+  int clapack_##P##getrs(int Order, int Trans, int N, int NRHS, const AT* A, int lda, const int* ipiv, AT* B, int ldb) {       \
+    return cl_getrs<T>("clapack_" #P "getrs", Order, Trans, N, NRHS, CP(T, A), lda, ipiv, MP(T, B), ldb); }                    \
+  int clapack_##P##getri(int Order, int N, AT* A, int lda, const int* ipiv) {                                                  \
+    int ierr = 0; const char* rout = "clapack_" #P "getri";                                                                    \
+    CL_CHECK(cl_order(rout, Order)); CL_CHECK(cl_nonneg(rout, 2, "N", N)); CL_CHECK(cl_ld(rout, 4, "lda", lda, N));           \
+    return ierr ? ierr : atl_getri<T>(Order, N, MP(T, A), lda, ipiv); }                                                        \
+  int clapack_##P##posv(int Order, int Uplo, int N, int NRHS, AT* A, int lda, AT* B, int ldb) {                                \
+    return cl_posv<T>("clapack_" #P "posv", true, Order, Uplo, N, NRHS, MP(T, A), lda, MP(T, B), ldb); }                       \
+  int clapack_##P##potrs(int Order, int Uplo, int N, int NRHS, const AT* A, int lda, AT* B, int ldb) {                         \
+    return cl_posv<T>("clapack_" #P "potrs", false, Order, Uplo, N, NRHS, const_cast<T*>(CP(T, A)), lda, MP(T, B), ldb); }     \
+  int clapack_##P##potri(int Order, int Uplo, int N, AT* A, int lda) {                                                         \
+    return cl_triop<T>("clapack_" #P "potri", 2, Order, Uplo, NonUnit, N, MP(T, A), lda); }                                    \
+  int clapack_##P##lauum(int Order, int Uplo, int N, AT* A, int lda) {                                                         \
+    return cl_triop<T>("clapack_" #P "lauum", 1, Order, Uplo, NonUnit, N, MP(T, A), lda); }                                    \
+  int clapack_##P##trtri(int Order, int Uplo, int Diag, int N, AT* A, int lda) {                                               \
+    return cl_triop<T>("clapack_" #P "trtri", 0, Order, Uplo, Diag, N, MP(T, A), lda); }                                       \
+  void ATL_##P##getrs(int Order, int Trans, int N, int NRHS, const RT* A, int lda, const int* ipiv, RT* B, int ldb) {          \
+    atl_getrs<T>(Order, Trans, N, NRHS, CP(T, A), lda, ipiv, MP(T, B), ldb); }                                                 \
+  void ATL_##P##potrs(int Order, int Uplo, int N, int NRHS, const RT* A, int lda, RT* B, int ldb) {                            \
+    atl_potrs<T>(Order, Uplo, N, NRHS, CP(T, A), lda, MP(T, B), ldb); }                                                        \
+  int ATL_##P##trtri(int Order, int Uplo, int Diag, int N, RT* A, int lda) { return atl_triop<T>(0, Order, Uplo, Diag, N, MP(T, A), lda); } \
+  void ATL_##P##lauum(int Order, int Uplo, int N, RT* A, int lda) { (void)atl_triop<T>(1, Order, Uplo, NonUnit, N, MP(T, A), lda); } \
+  int ATL_##P##getri(int Order, int N, RT* A, int lda, const int* ipiv, RT* wrk, int* lwrk) {                                  \
+    (void)wrk;                                                                                                                 \
+    if (lwrk && *lwrk == -1) { *lwrk = N * 64; return 0; }     /* workspace query (atlas-lp.base:217) */                       \
+    return atl_getri<T>(Order, N, MP(T, A), lda, ipiv); }                                                                      \
+  void P##getrs_(const char* tr, const int* n, const int* nrhs, const AT* A, const int* lda, const int* ipiv, AT* B,           \
+                 const int* ldb, int* info, size_t) {                                                                          \
+    f_getrs<T>(UP "GETRS", false, tr, n, nrhs, const_cast<T*>(CP(T, A)), lda, const_cast<int*>(ipiv), MP(T, B), ldb, info); }  \
+  void P##gesv_(const int* n, const int* nrhs, AT* A, const int* lda, int* ipiv, AT* B, const int* ldb, int* info) {           \
+    f_getrs<T>(UP "GESV ", true, "N", n, nrhs, MP(T, A), lda, ipiv, MP(T, B), ldb, info); }                                    \
+  void P##potrs_(const char* ul, const int* n, const int* nrhs, const AT* A, const int* lda, AT* B, const int* ldb, int* info, \
+                 size_t) { f_potrs<T>(UP "POTRS", false, ul, n, nrhs, const_cast<T*>(CP(T, A)), lda, MP(T, B), ldb, info); }   \
+  void P##posv_(const char* ul, const int* n, const int* nrhs, AT* A, const int* lda, AT* B, const int* ldb, int* info,        \
+                size_t) { f_potrs<T>(UP "POSV ", true, ul, n, nrhs, MP(T, A), lda, MP(T, B), ldb, info); }                     \
+  void P##trtri_(const char* ul, const char* dg, const int* n, AT* A, const int* lda, int* info, size_t, size_t) {             \
+    f_triop<T>(UP "TRTRI", 0, ul, dg, n, MP(T, A), lda, info); }                                                               \
+  void P##lauum_(const char* ul, const int* n, AT* A, const int* lda, int* info, size_t) {                                     \
+    f_triop<T>(UP "LAUUM", 1, ul, "N", n, MP(T, A), lda, info); }                                                              \
+  void P##potri_(const char* ul, const int* n, AT* A, const int* lda, int* info, size_t) {                                     \
+    f_triop<T>(UP "POTRI", 2, ul, "N", n, MP(T, A), lda, info); }                                                              \
+  void P##getri_(const int* n, AT* A, const int* lda, const int* ipiv, AT* work, const int* lwork, int* info) {                \
+    f_getri<T>(UP "GETRI", n, MP(T, A), lda, ipiv, MP(T, work), lwork, info); }
+SOLVE_API(s, float, float, float, "S")
+SOLVE_API(d, double, double, double, "D")
+SOLVE_API(c, cfloat, void, float, "C")
+SOLVE_API(z, cdouble, void, double, "Z")
+}

@@ -12,7 +12,8 @@
 #    this repo.  What IS built is the code the reference itself trusts in its
 #    testers: the reference BLAS ATL_Xref* (Antoine/atlrefblas.base), the tester generators /
 #    norms (Clint/atlas-tst.base) and the real recursive LAPACK drivers ATL_getrfC / ATL_getf2 /
-#    ATL_laswp / ATL_potrf{L,U} (Clint/atlas-lp.base) linked against that reference BLAS through
+#    ATL_laswp / ATL_potrf{L,U} and the solve/inverse layer ATL_getrs / potrs / trtri / lauum /
+#    getri (Clint/atlas-lp.base) linked against that reference BLAS through
 #    oracle/ref_shim/cblas_to_ref.c (our glue: cblas_* -> ATL_Xref*).
 #  * oracle/ref_shim/*.h are ours: the few configure-probed facts (type sizes, IEEE limits,
 #    L1 size) the sources need.
@@ -42,8 +43,15 @@ for t in s:SREAL d:DREAL c:SCPLX z:DCPLX; do
   p=${t%%:*}; D=${t##*:}
   for f in testing/ATL_gegen testing/ATL_epsilon testing/ATL_genrm1 testing/ATL_gediffnrm1 testing/ATL_synrm \
            testing/ATL_trnrm1 lapack/ATL_getrf lapack/ATL_getrfC lapack/ATL_getrfR lapack/ATL_getf2 lapack/ATL_laswp \
-           lapack/ATL_potrf lapack/ATL_potrfL lapack/ATL_potrfU; do
+           lapack/ATL_potrf lapack/ATL_potrfL lapack/ATL_potrfU \
+           lapack/ATL_getrs lapack/ATL_potrs lapack/ATL_trtri lapack/ATL_trtriCL lapack/ATL_trtriCU lapack/ATL_trtriRL \
+           lapack/ATL_trtriRU lapack/ATL_lauum lapack/ATL_getri lapack/ATL_getriC lapack/ATL_getriR; do
     gcc $CF -D$D -c $A/src/$f.c -o obj/${p}_$(basename $f).o
+  done
+  # ATL_lauum{L,U}.c are compiled twice by the reference: column-major and -DRowMajor_
+  for f in lauumL lauumU; do
+    gcc $CF -D$D -c $A/src/lapack/ATL_$f.c -o obj/${p}_${f}_C.o
+    gcc $CF -D$D -DRowMajor_ -c $A/src/lapack/ATL_$f.c -o obj/${p}_${f}_R.o
   done
   if [ $p = c ] || [ $p = z ]; then
     for f in testing/ATL_henrm lapack/ATL_potrfRL lapack/ATL_potrfRU auxil/ATL_cplxinvert auxil/ATL_cplxdivide; do

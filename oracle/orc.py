@@ -163,6 +163,27 @@ class Oracle(_Base):
     def potrf(self, pre, uplo, N, a, leaf=4):
         return getattr(self.lib, f"orc_{pre}potrf_rec")(uplo, N, _p(a), self._ld(a), leaf if not CPLX[pre] else 1)
 
+    # ---- solve / inverse layer; a, b are modified in place
+    def getrs(self, pre, order, trans, N, NRHS, a, ipiv, b):
+        ipiv = np.ascontiguousarray(ipiv, dtype=np.int32)
+        getattr(self.lib, f"orc_{pre}getrs")(order, trans, N, NRHS, _p(a), self._ld(a), _p(ipiv), _p(b), self._ld(b))
+
+    def potrs(self, pre, order, uplo, N, NRHS, a, b):
+        getattr(self.lib, f"orc_{pre}potrs")(order, uplo, N, NRHS, _p(a), self._ld(a), _p(b), self._ld(b))
+
+    def trtri(self, pre, order, uplo, diag, N, a):
+        return getattr(self.lib, f"orc_{pre}trtri")(order, uplo, diag, N, _p(a), self._ld(a))
+
+    def lauum(self, pre, order, uplo, N, a):
+        getattr(self.lib, f"orc_{pre}lauum")(order, uplo, N, _p(a), self._ld(a))
+
+    def potri(self, pre, order, uplo, N, a):
+        return getattr(self.lib, f"orc_{pre}potri")(order, uplo, N, _p(a), self._ld(a))
+
+    def getri(self, pre, order, N, a, ipiv, nb=4):
+        ipiv = np.ascontiguousarray(ipiv, dtype=np.int32)
+        return getattr(self.lib, f"orc_{pre}getri")(N, _p(a), self._ld(a), _p(ipiv), nb)
+
 
 class Ref(_Base):
     """The reference's own C (oracle/_ref/libatlref.so): ATL_Xref* BLAS, tester generators and
@@ -249,6 +270,32 @@ class Ref(_Base):
 
     def potrf(self, pre, uplo, N, a, leaf=None):
         return getattr(self.lib, f"ATL_{pre}potrf")(ColMajor, uplo, N, _p(a), self._ld(a))
+
+    # ---- solve / inverse layer: the reference's own ATL_getrs / potrs / trtri / lauum / getri
+    def getrs(self, pre, order, trans, N, NRHS, a, ipiv, b):
+        ipiv = np.ascontiguousarray(ipiv, dtype=np.int32)
+        getattr(self.lib, f"ATL_{pre}getrs")(order, trans, N, NRHS, _p(a), self._ld(a), _p(ipiv), _p(b), self._ld(b))
+
+    def potrs(self, pre, order, uplo, N, NRHS, a, b):
+        getattr(self.lib, f"ATL_{pre}potrs")(order, uplo, N, NRHS, _p(a), self._ld(a), _p(b), self._ld(b))
+
+    def trtri(self, pre, order, uplo, diag, N, a):
+        return getattr(self.lib, f"ATL_{pre}trtri")(order, uplo, diag, N, _p(a), self._ld(a))
+
+    def lauum(self, pre, order, uplo, N, a):
+        getattr(self.lib, f"ATL_{pre}lauum")(order, uplo, N, _p(a), self._ld(a))
+
+    def potri(self, pre, order, uplo, N, a):
+        ierr = self.trtri(pre, order, uplo, NonUnit, N, a)     # clapack_Xpotri = trtri + lauum
+        if not ierr:
+            self.lauum(pre, order, uplo, N, a)
+        return ierr
+
+    def getri(self, pre, order, N, a, ipiv, nb=4):
+        ipiv = np.ascontiguousarray(ipiv, dtype=np.int32)
+        wrk = np.zeros(max(N * nb, 1), dtype=DT[pre])
+        lwrk = C.c_int(N * nb)
+        return getattr(self.lib, f"ATL_{pre}getri")(order, N, _p(a), self._ld(a), _p(ipiv), _p(wrk), C.byref(lwrk))
 
 
 # ------------------------------------------------------------------------------------------

@@ -537,6 +537,178 @@ int FN(potrf_rec)(int uplo, int N, S* A, int lda, int leaf) {
   return ierr ? ierr + Nleft : 0;
 }
 
+
+/* ---- solve / inverse layer on the factors ------------------------------------
+   Enum values: Order 101/102, Trans 111/112/113, Uplo 121/122, Diag 131/132, Side 141/142.
+   A RowMajor matrix is handled as the reference does: cblas_trsm(RowMajor, Right, uplo, t) is the
+   column-major Left solve with the other triangle on the same memory. */
+
+/* ATL_getrs, Clint/atlas-lp.base:1631-1716 */
+void FN(getrs)(int order, int trans, int N, int NRHS, const S* A, int lda, const int* ipiv, S* B, int ldb) {
+  if (!N || !NRHS) return;
+  const S one = S_ONE;
+  if (order == 102) {
+    if (trans == 111) {
+      FN(laswp)(NRHS, B, ldb, 0, N, ipiv, 1);
+      FN(trsm)(141, 122, 111, 132, N, NRHS, &one, A, lda, B, ldb);
+      FN(trsm)(141, 121, 111, 131, N, NRHS, &one, A, lda, B, ldb);
+    } else {
+      FN(trsm)(141, 121, trans, 131, N, NRHS, &one, A, lda, B, ldb);
+      FN(trsm)(141, 122, trans, 132, N, NRHS, &one, A, lda, B, ldb);
+      FN(laswp)(NRHS, B, ldb, 0, N, ipiv, -1);
+    }
+  } else {
+    if (trans == 111) {   /* RowMajor Right,Lower,Trans,NonUnit ; Right,Upper,Trans,Unit ; laswp(-1) */
+      FN(trsm)(141, 121, 112, 131, N, NRHS, &one, A, lda, B, ldb);
+      FN(trsm)(141, 122, 112, 132, N, NRHS, &one, A, lda, B, ldb);
+      FN(laswp)(NRHS, B, ldb, 0, N, ipiv, -1);
+    } else {              /* laswp(+1) ; RowMajor Right,Upper,NoTrans,Unit ; Right,Lower,NoTrans,NonUnit */
+      FN(laswp)(NRHS, B, ldb, 0, N, ipiv, 1);
+      FN(trsm)(141, 122, 111, 132, N, NRHS, &one, A, lda, B, ldb);
+      FN(trsm)(141, 121, 111, 131, N, NRHS, &one, A, lda, B, ldb);
+    }
+  }
+}
+
+/* ATL_potrs, Clint/atlas-lp.base:969-1051 */
+void FN(potrs)(int order, int uplo, int N, int NRHS, const S* A, int lda, S* B, int ldb) {
+  if (!N || !NRHS) return;
+  const S one = S_ONE;
+#ifdef ORC_CPLX
+  const int tr = 113;
+#else
+  const int tr = 112;
+#endif
+  if (order == 102) {
+    if (uplo == 121) {
+      FN(trsm)(141, 121, tr, 131, N, NRHS, &one, A, lda, B, ldb);
+      FN(trsm)(141, 121, 111, 131, N, NRHS, &one, A, lda, B, ldb);
+    } else {
+      FN(trsm)(141, 122, 111, 131, N, NRHS, &one, A, lda, B, ldb);
+      FN(trsm)(141, 122, tr, 131, N, NRHS, &one, A, lda, B, ldb);
+    }
+  } else {
+#ifdef ORC_CPLX
+    for (int j = 0; j < NRHS; j++) for (int i = 0; i < N; i++) EL(B, ldb, i, j).im = -EL(B, ldb, i, j).im;
+#endif
+    if (uplo == 121) {   /* RowMajor Right,Upper,NoTrans ; Right,Upper,MyTrans */
+      FN(trsm)(141, 122, 111, 131, N, NRHS, &one, A, lda, B, ldb);
+      FN(trsm)(141, 122, tr, 131, N, NRHS, &one, A, lda, B, ldb);
+    } else {             /* RowMajor Right,Lower,MyTrans ; Right,Lower,NoTrans */
+      FN(trsm)(141, 121, tr, 131, N, NRHS, &one, A, lda, B, ldb);
+      FN(trsm)(141, 121, 111, 131, N, NRHS, &one, A, lda, B, ldb);
+    }
+#ifdef ORC_CPLX
+    for (int j = 0; j < NRHS; j++) for (int i = 0; i < N; i++) EL(B, ldb, i, j).im = -EL(B, ldb, i, j).im;
+#endif
+  }
+}
+
+/* ATL_trtriCL / ATL_trtriCU, Clint/atlas-lp.base:1902-2199 (column-major; the closed forms for
+   N <= 4 compute the same quantities as the N == 1 leaf reached by this recursion) */
+static void FN(trtri_rec)(int uplo, int diag, int N, S* A, int lda) {
+  if (N <= 0) return;
+  if (N == 1) { if (diag == 131) A[0] = S_INV(A[0]); return; }
+  const int Nleft = N >> 1, Nright = N - Nleft;
+  const S one = S_ONE, mone = S_FROMR(-1);
+  S* Atr = &EL(A, lda, Nleft, Nleft);
+  if (uplo == 122) {
+    S* Age = &EL(A, lda, Nleft, 0);
+    FN(trsm)(142, 122, 111, diag, Nright, Nleft, &one, A, lda, Age, lda);
+    FN(trsm)(141, 122, 111, diag, Nright, Nleft, &mone, Atr, lda, Age, lda);
+  } else {
+    S* Age = &EL(A, lda, 0, Nleft);
+    FN(trsm)(142, 121, 111, diag, Nleft, Nright, &one, Atr, lda, Age, lda);
+    FN(trsm)(141, 121, 111, diag, Nleft, Nright, &mone, A, lda, Age, lda);
+  }
+  FN(trtri_rec)(uplo, diag, Nleft, A, lda);
+  FN(trtri_rec)(uplo, diag, Nright, Atr, lda);
+}
+/* ATL_trtri, :2341-2381: singularity check first (A untouched on failure) */
+int FN(trtri)(int order, int uplo, int diag, int N, S* A, int lda) {
+  if (N <= 0) return 0;
+  if (diag == 131)
+    for (int i = 0; i < N; i++) if (S_ISZERO(EL(A, lda, i, i))) return i + 1;
+  FN(trtri_rec)(order == 102 ? uplo : (uplo == 121 ? 122 : 121), diag, N, A, lda);
+  return 0;
+}
+
+/* ATL_lauumCL / ATL_lauumCU, Clint/atlas-lp.base:221-311 */
+static void FN(lauum_rec)(int uplo, int N, S* A, int lda) {
+  if (N <= 0) return;
+  if (N == 1) {
+#ifdef ORC_CPLX
+    A[0] = MK(A[0].re * A[0].re + A[0].im * A[0].im, 0);
+#else
+    A[0] = A[0] * A[0];
+#endif
+    return;
+  }
+  const int Nleft = N >> 1, Nright = N - Nleft;
+  const S one = S_ONE;
+  S* U1 = &EL(A, lda, Nleft, Nleft);
+  FN(lauum_rec)(uplo, Nleft, A, lda);
+  if (uplo == 122) {
+    S* G = &EL(A, lda, Nleft, 0);
+#ifdef ORC_CPLX
+    FN(herk)(122, 113, Nleft, Nright, (R)1, G, lda, (R)1, A, lda);
+    FN(trmm)(141, 122, 113, 131, Nright, Nleft, &one, U1, lda, G, lda);
+#else
+    FN(syrk)(122, 112, Nleft, Nright, &one, G, lda, &one, A, lda);
+    FN(trmm)(141, 122, 112, 131, Nright, Nleft, &one, U1, lda, G, lda);
+#endif
+  } else {
+    S* G = &EL(A, lda, 0, Nleft);
+#ifdef ORC_CPLX
+    FN(herk)(121, 111, Nleft, Nright, (R)1, G, lda, (R)1, A, lda);
+    FN(trmm)(142, 121, 113, 131, Nleft, Nright, &one, U1, lda, G, lda);
+#else
+    FN(syrk)(121, 111, Nleft, Nright, &one, G, lda, &one, A, lda);
+    FN(trmm)(142, 121, 112, 131, Nleft, Nright, &one, U1, lda, G, lda);
+#endif
+  }
+  FN(lauum_rec)(uplo, Nright, U1, lda);
+}
+void FN(lauum)(int order, int uplo, int N, S* A, int lda) {
+  FN(lauum_rec)(order == 102 ? uplo : (uplo == 121 ? 122 : 121), N, A, lda);
+}
+/* clapack_Xpotri, Clint/atlas-clp.base:355-357 */
+int FN(potri)(int order, int uplo, int N, S* A, int lda) {
+  int ierr = FN(trtri)(order, uplo, 131, N, A, lda);
+  if (!ierr) FN(lauum)(order, uplo, N, A, lda);
+  return ierr;
+}
+
+/* ATL_getriC, Clint/atlas-lp.base:135-201, with block size nb and our own workspace; the
+   RowMajor routine (ATL_getriR, :16-108) performs the same operations on the same memory. */
+int FN(getri)(int N, S* A, int lda, const int* ipiv, int nb) {
+  int iret = FN(trtri)(102, 121, 131, N, A, lda);
+  if (iret || N <= 1) return iret;
+  if (nb < 1) nb = 1;
+  S* wrk = (S*)malloc(sizeof(S) * (size_t)N * (size_t)nb);
+  const S one = S_ONE, none = S_FROMR(-1);
+  int jb = N - (N / nb) * nb;
+  if (!jb) jb = nb;
+  int J = N - jb;
+  S* Ac = &EL(A, lda, 0, J);
+  for (int j = 0; j < jb; j++) for (int i = j + 1; i < jb; i++) { EL(wrk, jb, i, j) = EL(Ac, lda, J + i, j); EL(Ac, lda, J + i, j) = S_ZERO; }
+  FN(trsm)(142, 122, 111, 132, N, jb, &one, wrk, jb, Ac, lda);
+  while (J) {
+    J -= nb;
+    Ac = &EL(A, lda, 0, J);
+    const int nright = N - J;
+    for (int j = 0; j < nb; j++) for (int i = j + 1; i < nright; i++) { EL(wrk, nright, i, j) = EL(Ac, lda, J + i, j); EL(Ac, lda, J + i, j) = S_ZERO; }
+    FN(gemm)(111, 111, N, nb, nright - nb, &none, &EL(Ac, lda, 0, nb), lda, wrk + nb, nright, &one, Ac, lda);
+    FN(trsm)(142, 122, 111, 132, N, nb, &one, wrk, nright, Ac, lda);
+  }
+  for (J = N - 2; J >= 0; J--) {
+    const int p = ipiv[J];
+    if (p != J) for (int i = 0; i < N; i++) { S t = EL(A, lda, i, J); EL(A, lda, i, J) = EL(A, lda, i, p); EL(A, lda, i, p) = t; }
+  }
+  free(wrk);
+  return 0;
+}
+
 #undef S
 #undef MK
 #undef S_ZERO

@@ -38,6 +38,21 @@ void CB(herk)(const enum ATLAS_ORDER O, const enum ATLAS_UPLO U, const enum ATLA
                  alpha, A, lda, beta, C, ldc);
 }
 #endif
+void CB(trmm)(const enum ATLAS_ORDER O, const enum ATLAS_SIDE S, const enum ATLAS_UPLO U, const enum ATLAS_TRANS TA,
+              const enum ATLAS_DIAG D, const int M, const int N, const SCALAR alpha, const TYPE* A, const int lda,
+              TYPE* B, const int ldb) {
+  if (O == AtlasColMajor) REF(trmm)(S, U, TA, D, M, N, alpha, A, lda, B, ldb);
+  else REF(trmm)(S == AtlasLeft ? AtlasRight : AtlasLeft, U == AtlasUpper ? AtlasLower : AtlasUpper, TA, D, N, M,
+                 alpha, A, lda, B, ldb);
+}
+/* blocking hint of the solve/inverse drivers (the reference derives it from tuned GEMM tables) */
+int Mjoin(PATL, laGetB)(int M, int N, int K, int HINT) { return 4; }
+#if defined(SCPLX)
+/* ATL_potrs conjugates a RowMajor right-hand side with the REAL scal on the imaginary parts */
+void ATL_sscal(long N, const float alpha, float* X, long incX) { ATL_srefscal((int)N, alpha, X, (int)incX); }
+#elif defined(DCPLX)
+void ATL_dscal(long N, const double alpha, double* X, long incX) { ATL_drefscal((int)N, alpha, X, (int)incX); }
+#endif
 int Mjoin(Mjoin(cblas_i, PRE), amax)(const int N, const TYPE* X, const int incX) {
   return Mjoin(Mjoin(Mjoin(ATL_i, PRE), ref), amax)(N, X, incX);
 }
