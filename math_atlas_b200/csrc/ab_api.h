@@ -84,6 +84,9 @@ void getri_finish(int N, T* A, size_t lda, const int* d_ipiv);
 template <typename T>
 void conj_inplace(int M, int N, T* B, size_t ldb);
 
+// GEMMs launched by this host thread stay off the SMs of one GPC while on (see lapack.cu)
+void lu_reserve_sms(bool on);
+
 // Grow-only per-thread device workspace (freed by free_workspace()).
 void* workspace(size_t bytes, int slot = 0);
 void free_workspace();

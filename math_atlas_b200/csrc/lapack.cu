@@ -516,6 +516,10 @@ static void getrf_lookahead(int M, int N, T* A, size_t lda, int* d_ipiv, int* d_
   }
 }
 
+// Multi-GPU drivers (math_atlas_b200/dist.py): keep the look-ahead GPC free of update-GEMM CTAs so
+// that a collective's kernels posted beside a long update can always be scheduled.
+void lu_reserve_sms(bool on) { set_gemm_reserved(on ? cluster_reserved_mask() : nullptr); }
+
 template <typename T>
 void getrf(int M, int N, T* A, size_t lda, int* d_ipiv, int* d_info) {
   AB_CUDA_CHECK(cudaMemsetAsync(d_info, 0, sizeof(int), current_stream()));

@@ -20,6 +20,7 @@ The local work goes through the C ABI of libatlas_b200.so on device pointers in 
 (tests/test_dist_gloo.py), which is how the host-side logic is covered without GPUs.
 """
 import ctypes as C
+import os
 
 import torch
 import torch.distributed as dist
@@ -101,6 +102,13 @@ class CudaOps:
 
     def close(self):
         self.L.atlb200_set_async(0)
+
+    def reserve(self, on):
+        """Large GEMMs leave one GPC free while on: the broadcast posted just before a long trailing
+        update must not queue behind its persistent CTAs (measured: without this the 8-GPU LU ran
+        update and panel+broadcast back to back)."""
+        if os.environ.get("ATLB200_DIST_RESERVE", "1") != "0":
+            self.L.atlb200_reserve_sms(1 if on else 0)
 
     def getrf(self, M, N, a, lda, piv, info):
         getattr(self.L, f"atlb200_{self.pre}getrf_dev")(M, N, a, lda, piv.data_ptr(), info.data_ptr())
@@ -199,10 +207,20 @@ def pgetrf(pre, M, lay, A_loc, ld, ops, group=None, lookahead=True):
             ops.gemm(CblasNoTrans, CblasNoTrans, Mk - w, nc, w, -1.0, P.data_ptr() + w * P.element_size(), Mk,
                      addr(A_loc, k0, c0, ld), ld, 1.0, addr(A_loc, k0 + w, c0, ld), ld)
 
+    # ATLB200_DIST_TRACE=1: CUDA-event timeline of this rank's main stream, printed per step at the end
+    trace = os.environ.get("ATLB200_DIST_TRACE", "0") != "0" and dev.type == "cuda"
+    marks = []
+
+    def mark(k, tag):
+        if trace:
+            e = torch.cuda.Event(enable_timing=True); e.record(); marks.append((k, tag, e))
+
     buf, work = post(0)
     for k in range(nsteps):
+        mark(k, "enter")
         if work is not None:
             work.wait()
+        mark(k, "have_panel")
         k0, wc, w, Mk = geom(k)
         P = buf[:wc * Mk]
         tail = _tail_ints(buf, wc * Mk, lay.nb + 1)
@@ -213,14 +231,21 @@ def pgetrf(pre, M, lay, A_loc, ld, ops, group=None, lookahead=True):
         if nxt and lookahead and rank == lay.owner(k + 1):
             w1 = lay.width(k + 1)
             update(k, P, piv, t0, t0 + w1)          # bring the next panel up to date first ...
+            mark(k, "next_cols")
             nbuf, nwork = post(k + 1)               # ... factor it and start its broadcast ...
+            mark(k, "factored")
+            if lay.q > 1 and hasattr(ops, "reserve"):
+                ops.reserve(True)                   # (room for the broadcast's kernels beside the GEMM)
             update(k, P, piv, t0 + w1, lay.ncols_local)   # ... which overlaps the rest of the update
+            if lay.q > 1 and hasattr(ops, "reserve"):
+                ops.reserve(False)
         else:
             if nxt and lookahead:
                 nbuf, nwork = post(k + 1)           # receive the next panel while updating
             update(k, P, piv, t0, lay.ncols_local)
             if nxt and not lookahead:
                 nbuf, nwork = post(k + 1)
+        mark(k, "updated")
         if left_end > 0:                             # interchanges on the columns left of the panel
             ops.laswp(left_end, addr(A_loc, k0, 0, ld), ld, 0, w, piv)
         ipiv[k0:k0 + w] = piv + k0
@@ -228,6 +253,14 @@ def pgetrf(pre, M, lay, A_loc, ld, ops, group=None, lookahead=True):
         info_g.copy_(torch.where((info_g == 0) & (ik != 0), ik + k0, info_g))
         if nxt:
             buf, work = nbuf, nwork
+    if trace:
+        torch.cuda.synchronize()
+        t00 = marks[0][2]
+        rows = {}
+        for k, tag, e in marks:
+            rows.setdefault(k, []).append(f"{tag}={t00.elapsed_time(e):.2f}")
+        sel = [k for k in sorted(rows) if k < 10 or k % 16 == 0 or k > nsteps - 4]
+        print("\n".join(f"[pgetrf trace rank {rank}] step {k:3d} owner(k+1)={lay.owner(k + 1) if k + 1 < nsteps else -1}: " + " ".join(rows[k]) for k in sel), flush=True)
     return ipiv[:MN], int(info_g.item())
 
 
