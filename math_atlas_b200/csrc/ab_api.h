@@ -84,8 +84,8 @@ void getri_finish(int N, T* A, size_t lda, const int* d_ipiv);
 template <typename T>
 void conj_inplace(int M, int N, T* B, size_t ldb);
 
-// GEMMs launched by this host thread stay off the SMs of one GPC while on (see lapack.cu)
-void lu_reserve_sms(bool on);
+// large GEMMs launched by this host thread stay off n SMs (<= 16, one GPC) while n > 0 (see lapack.cu)
+void lu_reserve_sms(int n);
 
 // Grow-only per-thread device workspace (freed by free_workspace()).
 void* workspace(size_t bytes, int slot = 0);

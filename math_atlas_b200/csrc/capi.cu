@@ -680,7 +680,7 @@ CPLX_API(z, cdouble, double, "Z")
 // everything (matrix, pivots, info) is in device memory, work is only enqueued on the stream.
 extern "C" {
 void atlb200_set_async(int on) { g_async = on; }
-void atlb200_reserve_sms(int on) { lu_reserve_sms(on != 0); }
+void atlb200_reserve_sms(int n) { lu_reserve_sms(n); }
 #define DEV_API(P, T)                                                                                              \
   void atlb200_##P##getrf_dev(int M, int N, void* A, size_t lda, int* d_ipiv, int* d_info) {                       \
     getrf<T>(M, N, MP(T, A), lda, d_ipiv, d_info); }                                                                \

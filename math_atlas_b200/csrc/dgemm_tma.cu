@@ -198,6 +198,18 @@ dgemm_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     int m0, n0;
     tile_coords(tile, tiles_m, tiles_n, m0, n0);
 
+    if (!beta0) {
+      // bring this tile's C block (128 columns x 1 KiB) into L2 while the k loop runs: thread i of
+      // the 256 consumers takes column i/2, half i%2, four 128-byte lines
+      const int ctid = (int)threadIdx.x;               // consumer warps are 0..7
+      const int pc = n0 + (ctid >> 1), pr = m0 + (ctid & 1) * 64;
+      if (pc < N) {
+        const double* cp = C + (size_t)pc * ldc;
+#pragma unroll
+        for (int q = 0; q < 4; q++)
+          if (pr + q * 16 < M) asm volatile("prefetch.global.L2 [%0];" ::"l"(cp + pr + q * 16));
+      }
+    }
     double acc[8][4][2];
 #pragma unroll
     for (int i = 0; i < 8; i++)
@@ -235,11 +247,31 @@ dgemm_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     }
 
     // ---- epilogue: C = alpha*acc + beta*C (ablk2cmat, atlas-ammm.base:550), triangle mask for SYRK ----
+    // Eight dependent load->store rounds per thread (one per column; more loads in flight do not
+    // fit: 3 of the 9 warps share a 16K-register sub-partition, which caps the kernel at 168
+    // registers, 128 of them accumulators).  The rounds hit L2 because the C block was prefetched
+    // at the start of the tile; from DRAM they cost 9.6 us per tile, 12 % of a K=512 update.
+    const bool interior = (cmode == C_FULL) && (m0 + BM <= M) && (n0 + BN <= N);
 #pragma unroll
     for (int ni = 0; ni < 4; ni++) {
 #pragma unroll
       for (int e = 0; e < 2; e++) {
         const int n = n0 + wn * 32 + ni * 8 + 2 * t + e;
+        if (interior) {                      // no per-element tests: the eight loads of a column go out together
+          double* cc = C + (size_t)n * ldc + (m0 + wm * 64 + g);
+          double c8[8];
+          if (!beta0) {
+#pragma unroll
+            for (int mi = 0; mi < 8; mi++) c8[mi] = cc[mi * 8];
+          }
+#pragma unroll
+          for (int mi = 0; mi < 8; mi++) {
+            double r = alpha * acc[mi][ni][e];
+            if (!beta0) r += beta * c8[mi];
+            cc[mi * 8] = r;
+          }
+          continue;
+        }
         if (n >= N) continue;
         double* cc = C + (size_t)n * ldc;
 #pragma unroll

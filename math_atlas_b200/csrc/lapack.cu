@@ -516,9 +516,21 @@ static void getrf_lookahead(int M, int N, T* A, size_t lda, int* d_ipiv, int* d_
   }
 }
 
-// Multi-GPU drivers (math_atlas_b200/dist.py): keep the look-ahead GPC free of update-GEMM CTAs so
-// that a collective's kernels posted beside a long update can always be scheduled.
-void lu_reserve_sms(bool on) { set_gemm_reserved(on ? cluster_reserved_mask() : nullptr); }
+// Multi-GPU drivers (math_atlas_b200/dist.py): keep n SMs of the look-ahead GPC free of update-GEMM
+// CTAs (which then share their tiles dynamically), so that a collective's kernels posted beside a
+// long persistent update can always be scheduled.  n < 0: dynamic tile sharing only - for a rank whose
+// collective kernel is already resident: the GEMM CTAs it displaces start late and must not each
+// carry a full static share of the tiles.
+void lu_reserve_sms(int n) {
+  unsigned long long m[4] = {0, 0, 0, 0};
+  if (n < 0) { set_gemm_reserved(m); return; }     // no SM kept free, but tiles are shared dynamically
+  const unsigned long long* full = n > 0 ? cluster_reserved_mask() : nullptr;
+  if (!full) { set_gemm_reserved(nullptr); return; }
+  int taken = 0;
+  for (int i = 0; i < 256 && taken < n; i++)
+    if (full[i >> 6] >> (i & 63) & 1ull) { m[i >> 6] |= 1ull << (i & 63); taken++; }
+  set_gemm_reserved(m);
+}
 
 template <typename T>
 void getrf(int M, int N, T* A, size_t lda, int* d_ipiv, int* d_info) {

@@ -103,12 +103,16 @@ class CudaOps:
     def close(self):
         self.L.atlb200_set_async(0)
 
-    def reserve(self, on):
-        """Large GEMMs leave one GPC free while on: the broadcast posted just before a long trailing
-        update must not queue behind its persistent CTAs (measured: without this the 8-GPU LU ran
-        update and panel+broadcast back to back)."""
-        if os.environ.get("ATLB200_DIST_RESERVE", "1") != "0":
-            self.L.atlb200_reserve_sms(1 if on else 0)
+    def reserve(self, n):
+        """n > 0: large GEMMs leave n SMs free and share their tiles dynamically; n < 0: dynamic sharing
+        only; 0: off.  A persistent update GEMM otherwise holds every SM until it ends: on the panel
+        owner the broadcast posted beside it could not start (n > 0 fixes that), and on the receivers the
+        GEMM CTAs displaced by the already resident NCCL kernel would each run a full static share of the
+        tiles after everybody else (n < 0 fixes that).  Measured on 4 and 8 GPUs: without this a step
+        cost update + panel + broadcast, i.e. no overlap at all."""
+        if n > 0:
+            n = int(os.environ.get("ATLB200_DIST_RESERVE", n))
+        self.L.atlb200_reserve_sms(n)
 
     def getrf(self, M, N, a, lda, piv, info):
         getattr(self.L, f"atlb200_{self.pre}getrf_dev")(M, N, a, lda, piv.data_ptr(), info.data_ptr())
@@ -215,6 +219,9 @@ def pgetrf(pre, M, lay, A_loc, ld, ops, group=None, lookahead=True):
         if trace:
             e = torch.cuda.Event(enable_timing=True); e.record(); marks.append((k, tag, e))
 
+    overlap = lookahead and lay.q > 1 and hasattr(ops, "reserve")
+    if overlap:
+        ops.reserve(-1)     # every trailing update shares its tiles dynamically (see CudaOps.reserve)
     buf, work = post(0)
     for k in range(nsteps):
         mark(k, "enter")
@@ -234,11 +241,11 @@ def pgetrf(pre, M, lay, A_loc, ld, ops, group=None, lookahead=True):
             mark(k, "next_cols")
             nbuf, nwork = post(k + 1)               # ... factor it and start its broadcast ...
             mark(k, "factored")
-            if lay.q > 1 and hasattr(ops, "reserve"):
-                ops.reserve(True)                   # (room for the broadcast's kernels beside the GEMM)
+            if overlap:
+                ops.reserve(8)                      # (room for the broadcast's kernels, starting now, beside the GEMM)
             update(k, P, piv, t0 + w1, lay.ncols_local)   # ... which overlaps the rest of the update
-            if lay.q > 1 and hasattr(ops, "reserve"):
-                ops.reserve(False)
+            if overlap:
+                ops.reserve(-1)
         else:
             if nxt and lookahead:
                 nbuf, nwork = post(k + 1)           # receive the next panel while updating
@@ -253,6 +260,8 @@ def pgetrf(pre, M, lay, A_loc, ld, ops, group=None, lookahead=True):
         info_g.copy_(torch.where((info_g == 0) & (ik != 0), ik + k0, info_g))
         if nxt:
             buf, work = nbuf, nwork
+    if overlap:
+        ops.reserve(0)
     if trace:
         torch.cuda.synchronize()
         t00 = marks[0][2]
@@ -305,6 +314,9 @@ def ppotrf(pre, lay, A_loc, ld, ops, group=None, lookahead=True):
             ops.gemm(CblasNoTrans, tr, rest, wj, w, -1.0, P.data_ptr() + (off + wj) * es, Mk, P.data_ptr() + off * es, Mk,
                      1.0, addr(A_loc, j0 + wj, lj, ld), ld)
 
+    overlap = lookahead and lay.q > 1 and hasattr(ops, "reserve")
+    if overlap:
+        ops.reserve(8)      # as in pgetrf: the next panel's broadcast must be able to run beside the updates
     buf, work = post(0)
     for k in range(lay.nblocks):
         if work is not None:
@@ -331,4 +343,6 @@ def ppotrf(pre, lay, A_loc, ld, ops, group=None, lookahead=True):
         info_g.copy_(torch.where((info_g == 0) & (ik != 0), ik + k0, info_g))
         if nxt:
             buf, work = nbuf, nwork
+    if overlap:
+        ops.reserve(0)
     return int(info_g.item())
