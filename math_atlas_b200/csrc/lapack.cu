@@ -91,15 +91,6 @@ void laswp(int N, T* A, size_t lda, int K1, int K2, const int* d_piv, int inci) 
   AB_CUDA_CHECK(cudaGetLastError());
 }
 
-__global__ void ipiv_add_kernel(int* piv, int n, int add) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) piv[i] += add;
-}
-__global__ void info_merge_kernel(int* info, const int* sub, int add) {
-  // ierr = first failure: keep an earlier one, else take the sub-problem's (shifted)
-  if (*info == 0 && *sub != 0) *info = *sub + add;
-}
-
 // ------------------------------------------------------------------------------------- LU panel
 template <typename T> struct Safmin;
 template <> struct Safmin<float>   { static __device__ float v()  { return FLT_MIN; } };

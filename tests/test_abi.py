@@ -125,3 +125,69 @@ def test_f77_argument_errors(L):
     assert call(4, 5, 6, 3, 6, 4)[0] == 8
     assert call(4, 5, 6, 4, 5, 4)[0] == 10
     assert call(4, 5, 6, 4, 6, 3) == (13, "DGEMM ")
+
+
+@pytest.mark.parametrize("pre", "sdcz")
+def test_symm_syr2k_argument_errors(L, pre):
+    """numbering of Clint/cblas.base:237-586 (symm: Order, Side, Uplo, M, N, .., lda=8, ldb=10, ldc=13)"""
+    buf = np.zeros(64, dtype=np.complex128)
+    names = [("symm", ab.cblas_symm)] + ([("hemm", ab.cblas_hemm)] if pre in "cz" else [])
+    for nm, fn in names:
+        for over, want in ((dict(Order=0), 1), (dict(Side=0), 2), (dict(Uplo=0), 3), (dict(M=-1), 4), (dict(N=-1), 5),
+                           (dict(lda=3), 8), (dict(ldb=3), 10), (dict(ldc=3), 13)):
+            a = dict(Order=102, Side=141, Uplo=121, M=4, N=5, lda=4, ldb=4, ldc=4); a.update(over)
+            ab.last_xerbla()
+            fn(pre, a["Order"], a["Side"], a["Uplo"], a["M"], a["N"], 1.0, buf, a["lda"], buf, a["ldb"], 0.0, buf, a["ldc"])
+            assert ab.last_xerbla() == (want, f"cblas_{pre}{nm}"), (nm, over)
+    names = [("syr2k", ab.cblas_syr2k, 112)] + ([("her2k", ab.cblas_her2k, 113)] if pre in "cz" else [])
+    for nm, fn, tr in names:
+        for over, want in ((dict(Order=0), 1), (dict(Uplo=0), 2), (dict(Trans=0), 3), (dict(N=-1), 4), (dict(K=-1), 5),
+                           (dict(lda=3), 8), (dict(ldb=3), 10), (dict(ldc=3), 13)):
+            a = dict(Order=102, Uplo=121, Trans=111, N=4, K=5, lda=4, ldb=4, ldc=4); a.update(over)
+            ab.last_xerbla()
+            fn(pre, a["Order"], a["Uplo"], a["Trans"], a["N"], a["K"], 1.0, buf, a["lda"], buf, a["ldb"], 0.0, buf, a["ldc"])
+            assert ab.last_xerbla() == (want, f"cblas_{pre}{nm}"), (nm, over)
+    if pre in "cz":
+        ab.cblas_her2k(pre, 102, 121, 112, 4, 5, 1.0, buf, 5, buf, 5, 0.0, buf, 4)   # Trans is illegal for HER2K
+        assert ab.last_xerbla() == (3, f"cblas_{pre}her2k")
+
+
+@pytest.mark.parametrize("pre", "sdcz")
+def test_solve_layer_argument_errors(L, pre):
+    """numbering of Clint/atlas-clp.base:62-454; bad arguments return -argnum before any device work"""
+    buf = np.zeros(64, dtype=np.complex128); piv = np.zeros(8, dtype=np.int32)
+    assert ab.clapack_gesv(pre, 0, 4, 2, buf, 4, piv, buf, 4) == -1
+    assert ab.clapack_gesv(pre, 102, -1, 2, buf, 4, piv, buf, 4) == -2
+    assert ab.clapack_gesv(pre, 102, 4, -1, buf, 4, piv, buf, 4) == -3
+    assert ab.clapack_gesv(pre, 102, 4, 2, buf, 3, piv, buf, 4) == -5
+    assert ab.clapack_gesv(pre, 102, 4, 2, buf, 4, piv, buf, 3) == -8
+    assert ab.clapack_getrs(pre, 102, 0, 4, 2, buf, 4, piv, buf, 4) == -2
+    assert ab.clapack_getrs(pre, 102, 111, -1, 2, buf, 4, piv, buf, 4) == -3
+    assert ab.clapack_getrs(pre, 102, 111, 4, -1, buf, 4, piv, buf, 4) == -4
+    assert ab.clapack_getrs(pre, 102, 111, 4, 2, buf, 3, piv, buf, 4) == -6
+    assert ab.clapack_getrs(pre, 102, 111, 4, 2, buf, 4, piv, buf, 3) == -9
+    for fn in (ab.clapack_posv, ab.clapack_potrs):
+        assert fn(pre, 0, 121, 4, 2, buf, 4, buf, 4) == -1
+        assert fn(pre, 102, 0, 4, 2, buf, 4, buf, 4) == -2
+        assert fn(pre, 102, 121, -1, 2, buf, 4, buf, 4) == -3
+        assert fn(pre, 102, 121, 4, -1, buf, 4, buf, 4) == -4
+        assert fn(pre, 102, 121, 4, 2, buf, 3, buf, 4) == -6
+        assert fn(pre, 102, 121, 4, 2, buf, 4, buf, 3) == -8
+    for fn in (ab.clapack_potri, ab.clapack_lauum):
+        assert fn(pre, 0, 121, 4, buf, 4) == -1
+        assert fn(pre, 102, 0, 4, buf, 4) == -2
+        assert fn(pre, 102, 121, -1, buf, 4) == -3
+        assert fn(pre, 102, 121, 4, buf, 3) == -5
+    assert ab.clapack_trtri(pre, 0, 121, 131, 4, buf, 4) == -1
+    assert ab.clapack_trtri(pre, 102, 0, 131, 4, buf, 4) == -2
+    assert ab.clapack_trtri(pre, 102, 121, 0, 4, buf, 4) == -3
+    assert ab.clapack_trtri(pre, 102, 121, 131, -1, buf, 4) == -4
+    assert ab.clapack_trtri(pre, 102, 121, 131, 4, buf, 3) == -6
+    assert ab.clapack_getri(pre, 0, 4, buf, 4, piv) == -1
+    assert ab.clapack_getri(pre, 102, -1, buf, 4, piv) == -2
+    assert ab.clapack_getri(pre, 102, 4, buf, 3, piv) == -4
+    # empty problems return 0 without touching a device
+    assert ab.clapack_gesv(pre, 102, 0, 0, buf, 1, piv, buf, 1) == 0
+    assert ab.clapack_trtri(pre, 102, 121, 131, 0, buf, 1) == 0
+    assert ab.clapack_getri(pre, 102, 0, buf, 1, piv) == 0
+    ab.last_xerbla()
