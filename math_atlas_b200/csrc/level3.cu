@@ -14,6 +14,7 @@
 #include "dgemm_tma.h"
 #include "zgemm_tma.h"
 #include "sgemm_ffma.h"
+#include <cstdlib>
 #include <type_traits>
 
 namespace ab {
@@ -42,6 +43,10 @@ static void gemm_flags(int ta, int ca, int tb, int cb, int M, int N, int K, T al
       return;
   }
   if constexpr (std::is_same<T, float>::value) {
+    static const bool tc = [] { const char* v = getenv("ATLB200_SGEMM_TC"); return v ? atoi(v) != 0 : false; }();
+    if (tc && (double)M * N * K >= 16777216.0 && M >= 64 && N >= 64 && K >= 32 && !herk &&
+        sgemm_tc(ta, tb, M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, cmode, abort_flag))
+      return;
     if ((double)M * N >= 128.0 * 128.0 && K >= 8 && !herk &&
         sgemm_ffma(ta, tb, M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, cmode, abort_flag))
       return;

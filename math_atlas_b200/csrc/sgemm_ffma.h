@@ -10,3 +10,10 @@ bool sgemm_ffma(int ta, int tb, int M, int N, int K, float alpha, const float* A
 bool cgemm_ffma(int ta, int ca, int tb, int cb, int M, int N, int K, float2 alpha, const float2* A, size_t lda, const float2* B,
                 size_t ldb, float2 beta, float2* C, size_t ldc, int cmode, int herk, const int* abort_flag = nullptr);
 }  // namespace ab
+
+// SGEMM on the tcgen05 tensor cores with the 3xTF32 error-compensated split (sgemm_tc.cu); returns
+// false without doing anything when the packed operands would exceed the workspace budget.
+namespace ab {
+bool sgemm_tc(int ta, int tb, int M, int N, int K, float alpha, const float* A, size_t lda, const float* B, size_t ldb, float beta,
+              float* C, size_t ldc, int cmode, const int* abort_flag);
+}

@@ -1,0 +1,289 @@
+// SGEMM on the 5th-generation tensor cores: tcgen05.mma kind::tf32 with the accumulator in TMEM,
+// operands staged by TMA, FP32 accuracy recovered by the error-compensated split
+//     a = a_hi + a_lo,  a_hi = tf32(a),  a_lo = tf32(a - a_hi)          (a - a_hi is exact in FP32)
+//     a*b ~= a_hi*b_hi + a_hi*b_lo + a_lo*b_hi                          (the dropped a_lo*b_lo is < 2^-22 |ab|)
+// i.e. three tensor-core products per FP32 product ("3xTF32"): per-product error ~2^-21 |ab| against
+// 2^-24 for an FFMA, far inside the reference tester's bound 50*K*eps*|A||B| (a single TF32 product,
+// 2^-11, is not - which is why the FFMA kernel in sgemm_ffma.cu exists).  TF32 peak is 1.1 PFLOP/s
+// dense on B200, so the split still leaves ~5x the FP32 FFMA pipe (74 TFLOP/s).
+//
+// This is ATLAS's own structure: the split is done once per operand by a copy kernel that writes
+// K-major ("access-major") packed hi/lo panels - cm2am (Clint/atlas-ammm.base:544-570) - which also
+// canonicalises the four transpose cases, and the compute kernel (ammkern, :577) only ever sees
+// one layout.  The copy is O(N^2) HBM traffic against O(N^3) tensor work.
+//
+// Compute kernel: one CTA per 128x128 tile, 192 threads:
+//   warp 0   TMA producer: per k block of 32 the four 16 KB tiles A_hi, A_lo, B_hi, B_lo (128-byte rows,
+//            SWIZZLE_128B = the canonical K-major UMMA layout), 3-stage ring of 64 KB
+//   warp 1   allocates 128 TMEM columns; one elected lane issues 4 x 3 tcgen05.mma (K=8 each) per stage,
+//            tcgen05.commit releases the stage / publishes the finished accumulator
+//   warps 2-5  epilogue: tcgen05.ld (32 lanes x 32 columns per instruction), C = alpha*acc + beta*C
+#include "common.cuh"
+#include "sgemm_ffma.h"
+#include <cuda.h>
+#include <mutex>
+#include <cstdio>
+#include <cstdlib>
+
+namespace ab {
+namespace {
+
+constexpr int BM = 128, BN = 128, BK = 32, STAGES = 3, THREADS = 192, GROUP_M = 16;
+constexpr int TILE_BYTES = 128 * BK * 4;            // 16 KB: 128 rows of 128 bytes
+constexpr int STAGE_BYTES = 4 * TILE_BYTES;         // A_hi, A_lo, B_hi, B_lo
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*alignment*/ + 128 /*barriers*/;
+constexpr int TMEM_COLS = 128;
+
+// ---------------------------------------------------------------- device helpers (raw PTX)
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t a, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(a), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t a, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(a), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t a, uint32_t parity) {
+  uint32_t ok;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok) : "r"(a), "r"(parity) : "memory");
+  } while (!ok);
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* tm, int c0, int c1, uint32_t mbar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tm)), "r"(c0), "r"(c1), "r"(mbar) : "memory");
+}
+// shared-memory matrix descriptor, K-major, SWIZZLE_128B: 8-row groups 1024 B apart (SBO), version 1
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr) {
+  return (uint64_t)((saddr >> 4) & 0x3FFFu) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
+}
+// instruction descriptor: D=F32, A=B=TF32, both K-major, N=128, M=128
+constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_c, uint64_t da, uint64_t db, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_c), "l"(da), "l"(db), "r"(IDESC), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t mbar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(mbar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+        "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
+        "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+        "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr) : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// ---------------------------------------------------------------- cm2am: split + pack, K-major
+// P_hi/P_lo[r * Kp + k] for r < Rp, k < Kp (zero padded); op(X)(r,k) = X[r + k*ld] (kcontig=0) or X[k + r*ld] (kcontig=1)
+__global__ void __launch_bounds__(256) split_pack_kernel(int R, int K, int Rp, int Kp, const float* __restrict__ X, size_t ld, int kcontig,
+                                                         float* __restrict__ Ph, float* __restrict__ Pl) {
+  __shared__ float t[32][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;     // 32 x 8
+  const int r0 = blockIdx.y * 32, k0 = blockIdx.x * 32;
+  if (kcontig) {
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+      const int r = r0 + ty + 8 * i, k = k0 + tx;
+      t[ty + 8 * i][tx] = (r < R && k < K) ? X[(size_t)k + (size_t)r * ld] : 0.f;
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+      const int k = k0 + ty + 8 * i, r = r0 + tx;
+      t[tx][ty + 8 * i] = (r < R && k < K) ? X[(size_t)r + (size_t)k * ld] : 0.f;
+    }
+  }
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < 4; i++) {
+    const int r = r0 + ty + 8 * i, k = k0 + tx;
+    if (r < Rp && k < Kp) {
+      const float a = t[ty + 8 * i][tx];
+      uint32_t hb, lb;
+      asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hb) : "f"(a));
+      const float hi = __uint_as_float(hb);
+      asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(lb) : "f"(a - hi));
+      Ph[(size_t)r * Kp + k] = hi;
+      Pl[(size_t)r * Kp + k] = __uint_as_float(lb);
+    }
+  }
+}
+
+// ---------------------------------------------------------------- the tensor-core kernel
+__global__ void __launch_bounds__(THREADS, 1)
+sgemm_tc_kernel(const __grid_constant__ CUtensorMap mAh, const __grid_constant__ CUtensorMap mAl,
+                const __grid_constant__ CUtensorMap mBh, const __grid_constant__ CUtensorMap mBl, float* __restrict__ C, size_t ldc, int M,
+                int N, int KB, float alpha, float beta, int cmode, int tiles_m, int tiles_n, const int* __restrict__ abort_flag) {
+  if (abort_flag && *abort_flag) return;
+  // grouped rasterisation (same map as dgemm_tma.cu)
+  const int in_group = GROUP_M * tiles_n;
+  const int first_m = ((int)blockIdx.x / in_group) * GROUP_M;
+  const int gsz = min(tiles_m - first_m, GROUP_M);
+  const int m0 = (first_m + ((int)blockIdx.x % in_group) % gsz) * BM, n0 = (((int)blockIdx.x % in_group) / gsz) * BN;
+  if (cmode == C_UPPER && m0 > n0 + BN - 1) return;
+  if (cmode == C_LOWER && n0 > m0 + BM - 1) return;
+
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;        // SWIZZLE_128B tiles need 1024-byte alignment
+  const uint32_t bars = base + STAGES * STAGE_BYTES;                    // full[STAGES], empty[STAGES], accum
+  __shared__ uint32_t s_tmem;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; s++) { mbar_init(bars + 8 * s, 1); mbar_init(bars + 8 * (STAGES + s), 1); }
+    mbar_init(bars + 8 * (2 * STAGES), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem)), "n"(TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem = s_tmem;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      for (int kb = 0; kb < KB; kb++) {
+        const int s = kb % STAGES;
+        if (kb >= STAGES) mbar_wait(bars + 8 * (STAGES + s), ((kb / STAGES) - 1) & 1);
+        const uint32_t full = bars + 8 * s, dst = base + s * STAGE_BYTES;
+        mbar_expect_tx(full, STAGE_BYTES);
+        tma_load_2d(dst, &mAh, kb * BK, m0, full);
+        tma_load_2d(dst + TILE_BYTES, &mAl, kb * BK, m0, full);
+        tma_load_2d(dst + 2 * TILE_BYTES, &mBh, kb * BK, n0, full);
+        tma_load_2d(dst + 3 * TILE_BYTES, &mBl, kb * BK, n0, full);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      for (int kb = 0; kb < KB; kb++) {
+        const int s = kb % STAGES;
+        mbar_wait(bars + 8 * s, (kb / STAGES) & 1);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t sa = base + s * STAGE_BYTES;
+#pragma unroll
+        for (int k4 = 0; k4 < BK / 8; k4++) {
+          const uint64_t ah = umma_desc(sa + k4 * 32), al = umma_desc(sa + TILE_BYTES + k4 * 32);
+          const uint64_t bh = umma_desc(sa + 2 * TILE_BYTES + k4 * 32), bl = umma_desc(sa + 3 * TILE_BYTES + k4 * 32);
+          umma_tf32(tmem, al, bh, (kb > 0 || k4 > 0) ? 1u : 0u);     // small terms first
+          umma_tf32(tmem, ah, bl, 1u);
+          umma_tf32(tmem, ah, bh, 1u);
+        }
+        umma_commit(bars + 8 * (STAGES + s));      // the stage is free once these MMAs have read it
+      }
+      umma_commit(bars + 8 * (2 * STAGES));        // accumulator complete
+    }
+  } else {
+    // ---- epilogue: warp w may touch TMEM lanes 32*(w%4) .. +31 = tile rows
+    mbar_wait(bars + 8 * (2 * STAGES), 0);
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const int q = warp & 3;
+    const int m = m0 + q * 32 + lane;
+    const bool beta0 = (beta == 0.f);
+#pragma unroll 1
+    for (int c0 = 0; c0 < BN; c0 += 32) {
+      uint32_t r[32];
+      tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, r);
+      if (m < M) {
+#pragma unroll
+        for (int j = 0; j < 32; j++) {
+          const int n = n0 + c0 + j;
+          if (n >= N) continue;
+          if (cmode == C_UPPER && m > n) continue;
+          if (cmode == C_LOWER && m < n) continue;
+          float* c = C + (size_t)m + (size_t)n * ldc;
+          float v = alpha * __uint_as_float(r[j]);
+          if (!beta0) v += beta * *c;
+          *c = v;
+        }
+      }
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(TMEM_COLS) : "memory");
+  }
+}
+
+// ---------------------------------------------------------------- host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    AB_CUDA_CHECK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q));
+    if (!p || q != cudaDriverEntryPointSuccess) { fprintf(stderr, "atlas_b200: cuTensorMapEncodeTiled unavailable\n"); abort(); }
+    fn = reinterpret_cast<EncodeTiledFn>(p);
+  });
+  return fn;
+}
+// packed panel: Rp rows of Kp floats (K contiguous); box = 32 floats x 128 rows, 128-byte swizzle
+bool make_map(CUtensorMap* tm, const float* ptr, size_t Rp, size_t Kp) {
+  cuuint64_t dims[2] = {(cuuint64_t)Kp, (cuuint64_t)Rp};
+  cuuint64_t strides[1] = {(cuuint64_t)Kp * 4};
+  cuuint32_t box[2] = {(cuuint32_t)BK, 128};
+  cuuint32_t estr[2] = {1, 1};
+  return get_encode()(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(ptr), dims, strides, box, estr,
+                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+}  // namespace
+
+// op(A) is M x K, op(B) is K x N.  Returns false (nothing done) when the packed panels would not fit
+// the workspace budget; the caller then uses the FFMA kernel.
+bool sgemm_tc(int ta, int tb, int M, int N, int K, float alpha, const float* A, size_t lda, const float* B, size_t ldb, float beta,
+              float* C, size_t ldc, int cmode, const int* abort_flag) {
+  if (M <= 0 || N <= 0 || K <= 0) return false;
+  const size_t Mp = ((size_t)M + BM - 1) / BM * BM, Np = ((size_t)N + BN - 1) / BN * BN, Kp = ((size_t)K + BK - 1) / BK * BK;
+  const size_t bytes = 2 * sizeof(float) * (Mp + Np) * Kp;
+  static const size_t budget = [] { const char* v = getenv("ATLB200_SGEMM_TC_WS_GB"); return (size_t)(v ? atof(v) : 12.0) << 30; }();
+  if (bytes > budget) return false;
+  const long long tiles = (long long)(Mp / BM) * (long long)(Np / BN);
+  if (tiles > 0x7fffffffLL) return false;
+  // stream-ordered pool allocation: the look-ahead factorisations issue GEMMs from two streams
+  float* ws = nullptr;
+  AB_CUDA_CHECK(cudaMallocAsync(&ws, bytes, current_stream()));
+  float *Ah = ws, *Al = Ah + Mp * Kp, *Bh = Al + Mp * Kp, *Bl = Bh + Np * Kp;
+  // cm2am: op(A)(m,k) = A[m + k*lda] (NoTrans) or A[k + m*lda] (Trans: K contiguous); op(B)(k,n): rows of the packed
+  // panel are n, so B NoTrans (B[k + n*ldb]) is the K-contiguous case
+  split_pack_kernel<<<dim3((unsigned)(Kp / 32), (unsigned)(Mp / 32)), 256, 0, current_stream()>>>(M, K, (int)Mp, (int)Kp, A, lda, ta ? 1 : 0, Ah, Al);
+  split_pack_kernel<<<dim3((unsigned)(Kp / 32), (unsigned)(Np / 32)), 256, 0, current_stream()>>>(N, K, (int)Np, (int)Kp, B, ldb, tb ? 0 : 1, Bh, Bl);
+  count_launch(2);
+  AB_CUDA_CHECK(cudaGetLastError());
+  CUtensorMap mAh, mAl, mBh, mBl;
+  if (!make_map(&mAh, Ah, Mp, Kp) || !make_map(&mAl, Al, Mp, Kp) || !make_map(&mBh, Bh, Np, Kp) || !make_map(&mBl, Bl, Np, Kp)) {
+    AB_CUDA_CHECK(cudaFreeAsync(ws, current_stream()));
+    return false;
+  }
+  static bool attr = false;
+  if (!attr) { AB_CUDA_CHECK(cudaFuncSetAttribute(sgemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES)); attr = true; }
+  sgemm_tc_kernel<<<(unsigned)tiles, THREADS, SMEM_BYTES, current_stream()>>>(mAh, mAl, mBh, mBl, C, ldc, M, N, (int)(Kp / BK), alpha, beta, cmode,
+                                                                               (int)(Mp / BM), (int)(Np / BN), abort_flag);
+  count_launch();
+  AB_CUDA_CHECK(cudaGetLastError());
+  AB_CUDA_CHECK(cudaFreeAsync(ws, current_stream()));
+  return true;
+}
+
+}  // namespace ab
