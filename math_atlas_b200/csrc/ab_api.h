@@ -89,6 +89,7 @@ void lu_reserve_sms(int n);
 
 // Grow-only per-thread device workspace (freed by free_workspace()).
 void* workspace(size_t bytes, int slot = 0);
+void keep_pool_cached();   // cudaMallocAsync pool keeps its memory between calls
 void free_workspace();
 long long launch_count();
 void reset_launch_count();

@@ -86,17 +86,13 @@ static bool is_device_ptr(const void* p) {
 static void init_pool_once() {
   static std::once_flag once;
   std::call_once(once, [] {
-    int dev = 0, n = 0;
+    int n = 0;
     if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0) {
       fprintf(stderr, "atlas_b200: no CUDA device available - this library has no CPU fallback\n");
       abort();
     }
-    AB_CUDA_CHECK(cudaGetDevice(&dev));
-    cudaMemPool_t pool;
-    AB_CUDA_CHECK(cudaDeviceGetDefaultMemPool(&pool, dev));
-    unsigned long long keep = ~0ull;   // keep staged buffers cached between calls
-    AB_CUDA_CHECK(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
   });
+  keep_pool_cached();   // keep staged buffers cached between calls
 }
 
 // A rows x cols column-major operand that may live on the host: dev() is always a device pointer.

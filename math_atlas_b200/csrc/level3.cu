@@ -43,7 +43,7 @@ static void gemm_flags(int ta, int ca, int tb, int cb, int M, int N, int K, T al
       return;
   }
   if constexpr (std::is_same<T, float>::value) {
-    static const bool tc = [] { const char* v = getenv("ATLB200_SGEMM_TC"); return v ? atoi(v) != 0 : false; }();
+    static const bool tc = [] { const char* v = getenv("ATLB200_SGEMM_TC"); return v ? atoi(v) != 0 : true; }();
     if (tc && (double)M * N * K >= 16777216.0 && M >= 64 && N >= 64 && K >= 32 && !herk &&
         sgemm_tc(ta, tb, M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, cmode, abort_flag))
       return;

@@ -47,6 +47,20 @@ void* workspace(size_t bytes, int slot) {
   return s.ptr[slot];
 }
 
+// Stream-ordered allocations (cudaMallocAsync) are served from the device's default pool; keep what
+// it has grown to between calls instead of returning it to the driver at every synchronisation.
+void keep_pool_cached() {
+  static thread_local int done_dev = -1;
+  int dev = 0;
+  AB_CUDA_CHECK(cudaGetDevice(&dev));
+  if (done_dev == dev) return;
+  done_dev = dev;
+  cudaMemPool_t pool;
+  AB_CUDA_CHECK(cudaDeviceGetDefaultMemPool(&pool, dev));
+  unsigned long long keep = ~0ull;
+  AB_CUDA_CHECK(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
+}
+
 void free_workspace() {
   Slots& s = g_slots;
   for (int i = 0; i < Slots::N; i++)

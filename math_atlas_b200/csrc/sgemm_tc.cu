@@ -12,14 +12,16 @@
 // canonicalises the four transpose cases, and the compute kernel (ammkern, :577) only ever sees
 // one layout.  The copy is O(N^2) HBM traffic against O(N^3) tensor work.
 //
-// Compute kernel: one CTA per 128x128 tile, 192 threads:
-//   warp 0   TMA producer: per k block of 32 the four 16 KB tiles A_hi, A_lo, B_hi, B_lo (128-byte rows,
-//            SWIZZLE_128B = the canonical K-major UMMA layout), 3-stage ring of 64 KB
-//   warp 1   allocates 128 TMEM columns; one elected lane issues 4 x 3 tcgen05.mma (K=8 each) per stage,
+// Compute kernel: one CTA per 128x256 tile (operand bytes per flop 25 % below 128x128: the kernel is
+// bound by the L2 -> shared-memory feed, not by the tensor pipe), 192 threads:
+//   warp 0   TMA producer: per k block of 32 the four tiles A_hi, A_lo (128 rows), B_hi, B_lo (256 rows) of
+//            128-byte rows, SWIZZLE_128B = the canonical K-major UMMA layout; 2-stage ring of 96 KB
+//   warp 1   allocates 256 TMEM columns; one elected lane issues 4 x 3 tcgen05.mma (K=8 each) per stage,
 //            tcgen05.commit releases the stage / publishes the finished accumulator
 //   warps 2-5  epilogue: tcgen05.ld (32 lanes x 32 columns per instruction), C = alpha*acc + beta*C
 #include "common.cuh"
 #include "sgemm_ffma.h"
+#include "ab_api.h"
 #include <cuda.h>
 #include <mutex>
 #include <cstdio>
@@ -28,11 +30,16 @@
 namespace ab {
 namespace {
 
-constexpr int BM = 128, BN = 128, BK = 32, STAGES = 3, THREADS = 192, GROUP_M = 16;
-constexpr int TILE_BYTES = 128 * BK * 4;            // 16 KB: 128 rows of 128 bytes
-constexpr int STAGE_BYTES = 4 * TILE_BYTES;         // A_hi, A_lo, B_hi, B_lo
+#ifndef AB_STC_BN
+#define AB_STC_BN 256
+#endif
+constexpr int BM = 128, BN = AB_STC_BN, BK = 32, THREADS = 192, GROUP_M = 16;
+constexpr int A_TILE_BYTES = BM * BK * 4;           // 16 KB: 128 rows of 128 bytes
+constexpr int B_TILE_BYTES = BN * BK * 4;           // 16 or 32 KB
+constexpr int STAGE_BYTES = 2 * A_TILE_BYTES + 2 * B_TILE_BYTES;   // A_hi, A_lo, B_hi, B_lo
+constexpr int STAGES = (192 * 1024) / STAGE_BYTES;  // 3 (BN=128) or 2 (BN=256)
 constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*alignment*/ + 128 /*barriers*/;
-constexpr int TMEM_COLS = 128;
+constexpr int TMEM_COLS = BN;
 
 // ---------------------------------------------------------------- device helpers (raw PTX)
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -52,16 +59,16 @@ __device__ __forceinline__ void mbar_wait(uint32_t a, uint32_t parity) {
         : "=r"(ok) : "r"(a), "r"(parity) : "memory");
   } while (!ok);
 }
-__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* tm, int c0, int c1, uint32_t mbar) {
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* tm, int c0, int c1, int c2, uint32_t mbar) {
   asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
-      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tm)), "r"(c0), "r"(c1), "r"(mbar) : "memory");
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tm)), "r"(c0), "r"(c1), "r"(c2), "r"(mbar) : "memory");
 }
 // shared-memory matrix descriptor, K-major, SWIZZLE_128B: 8-row groups 1024 B apart (SBO), version 1
 __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr) {
   return (uint64_t)((saddr >> 4) & 0x3FFFu) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
 }
-// instruction descriptor: D=F32, A=B=TF32, both K-major, N=128, M=128
+// instruction descriptor: D=F32, A=B=TF32, both K-major, N=BN, M=128
 constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
 __device__ __forceinline__ void umma_tf32(uint32_t tmem_c, uint64_t da, uint64_t db, uint32_t accumulate) {
   asm volatile(
@@ -87,7 +94,9 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
 }
 
 // ---------------------------------------------------------------- cm2am: split + pack, K-major
-// P_hi/P_lo[r * Kp + k] for r < Rp, k < Kp (zero padded); op(X)(r,k) = X[r + k*ld] (kcontig=0) or X[k + r*ld] (kcontig=1)
+// Access-major panels: P_hi/P_lo[((k/32) * Rp + r) * 32 + k%32] for r < Rp, k < Kp (zero padded), so the 128 x 32
+// (256 x 32) block one TMA instruction fetches is one contiguous 16 (32) KB piece of memory - ATLAS's block-major
+// copy format.  op(X)(r,k) = X[r + k*ld] (kcontig=0) or X[k + r*ld] (kcontig=1)
 __global__ void __launch_bounds__(256) split_pack_kernel(int R, int K, int Rp, int Kp, const float* __restrict__ X, size_t ld, int kcontig,
                                                          float* __restrict__ Ph, float* __restrict__ Pl) {
   __shared__ float t[32][33];
@@ -116,8 +125,9 @@ __global__ void __launch_bounds__(256) split_pack_kernel(int R, int K, int Rp, i
       asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hb) : "f"(a));
       const float hi = __uint_as_float(hb);
       asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(lb) : "f"(a - hi));
-      Ph[(size_t)r * Kp + k] = hi;
-      Pl[(size_t)r * Kp + k] = __uint_as_float(lb);
+      const size_t o = ((size_t)blockIdx.x * Rp + r) * 32 + tx;      // blockIdx.x = k / 32
+      Ph[o] = hi;
+      Pl[o] = __uint_as_float(lb);
     }
   }
 }
@@ -163,10 +173,10 @@ sgemm_tc_kernel(const __grid_constant__ CUtensorMap mAh, const __grid_constant__
         if (kb >= STAGES) mbar_wait(bars + 8 * (STAGES + s), ((kb / STAGES) - 1) & 1);
         const uint32_t full = bars + 8 * s, dst = base + s * STAGE_BYTES;
         mbar_expect_tx(full, STAGE_BYTES);
-        tma_load_2d(dst, &mAh, kb * BK, m0, full);
-        tma_load_2d(dst + TILE_BYTES, &mAl, kb * BK, m0, full);
-        tma_load_2d(dst + 2 * TILE_BYTES, &mBh, kb * BK, n0, full);
-        tma_load_2d(dst + 3 * TILE_BYTES, &mBl, kb * BK, n0, full);
+        tma_load_3d(dst, &mAh, 0, m0, kb, full);
+        tma_load_3d(dst + A_TILE_BYTES, &mAl, 0, m0, kb, full);
+        tma_load_3d(dst + 2 * A_TILE_BYTES, &mBh, 0, n0, kb, full);
+        tma_load_3d(dst + 2 * A_TILE_BYTES + B_TILE_BYTES, &mBl, 0, n0, kb, full);
       }
     }
   } else if (warp == 1) {
@@ -178,8 +188,8 @@ sgemm_tc_kernel(const __grid_constant__ CUtensorMap mAh, const __grid_constant__
         const uint32_t sa = base + s * STAGE_BYTES;
 #pragma unroll
         for (int k4 = 0; k4 < BK / 8; k4++) {
-          const uint64_t ah = umma_desc(sa + k4 * 32), al = umma_desc(sa + TILE_BYTES + k4 * 32);
-          const uint64_t bh = umma_desc(sa + 2 * TILE_BYTES + k4 * 32), bl = umma_desc(sa + 3 * TILE_BYTES + k4 * 32);
+          const uint64_t ah = umma_desc(sa + k4 * 32), al = umma_desc(sa + A_TILE_BYTES + k4 * 32);
+          const uint64_t bh = umma_desc(sa + 2 * A_TILE_BYTES + k4 * 32), bl = umma_desc(sa + 2 * A_TILE_BYTES + B_TILE_BYTES + k4 * 32);
           umma_tf32(tmem, al, bh, (kb > 0 || k4 > 0) ? 1u : 0u);     // small terms first
           umma_tf32(tmem, ah, bl, 1u);
           umma_tf32(tmem, ah, bh, 1u);
@@ -237,13 +247,13 @@ EncodeTiledFn get_encode() {
   });
   return fn;
 }
-// packed panel: Rp rows of Kp floats (K contiguous); box = 32 floats x 128 rows, 128-byte swizzle
-bool make_map(CUtensorMap* tm, const float* ptr, size_t Rp, size_t Kp) {
-  cuuint64_t dims[2] = {(cuuint64_t)Kp, (cuuint64_t)Rp};
-  cuuint64_t strides[1] = {(cuuint64_t)Kp * 4};
-  cuuint32_t box[2] = {(cuuint32_t)BK, 128};
-  cuuint32_t estr[2] = {1, 1};
-  return get_encode()(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(ptr), dims, strides, box, estr,
+// packed panel [Kp/32][Rp][32]; box = 32 floats x box_rows rows x 1 k block, 128-byte swizzle
+bool make_map(CUtensorMap* tm, const float* ptr, size_t Rp, size_t Kp, int box_rows) {
+  cuuint64_t dims[3] = {32, (cuuint64_t)Rp, (cuuint64_t)(Kp / 32)};
+  cuuint64_t strides[2] = {128, (cuuint64_t)Rp * 128};
+  cuuint32_t box[3] = {32, (cuuint32_t)box_rows, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  return get_encode()(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(ptr), dims, strides, box, estr,
                       CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                       CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
@@ -263,16 +273,22 @@ bool sgemm_tc(int ta, int tb, int M, int N, int K, float alpha, const float* A, 
   if (tiles > 0x7fffffffLL) return false;
   // stream-ordered pool allocation: the look-ahead factorisations issue GEMMs from two streams
   float* ws = nullptr;
+  keep_pool_cached();
   AB_CUDA_CHECK(cudaMallocAsync(&ws, bytes, current_stream()));
   float *Ah = ws, *Al = Ah + Mp * Kp, *Bh = Al + Mp * Kp, *Bl = Bh + Np * Kp;
   // cm2am: op(A)(m,k) = A[m + k*lda] (NoTrans) or A[k + m*lda] (Trans: K contiguous); op(B)(k,n): rows of the packed
   // panel are n, so B NoTrans (B[k + n*ldb]) is the K-contiguous case
+  static const bool trace = getenv("ATLB200_SGEMM_TC_TRACE") != nullptr;
+  cudaEvent_t ev[4];
+  if (trace) { for (auto& e : ev) cudaEventCreate(&e); cudaEventRecord(ev[0], current_stream()); }
   split_pack_kernel<<<dim3((unsigned)(Kp / 32), (unsigned)(Mp / 32)), 256, 0, current_stream()>>>(M, K, (int)Mp, (int)Kp, A, lda, ta ? 1 : 0, Ah, Al);
+  if (trace) cudaEventRecord(ev[1], current_stream());
   split_pack_kernel<<<dim3((unsigned)(Kp / 32), (unsigned)(Np / 32)), 256, 0, current_stream()>>>(N, K, (int)Np, (int)Kp, B, ldb, tb ? 0 : 1, Bh, Bl);
   count_launch(2);
   AB_CUDA_CHECK(cudaGetLastError());
+  if (trace) cudaEventRecord(ev[2], current_stream());
   CUtensorMap mAh, mAl, mBh, mBl;
-  if (!make_map(&mAh, Ah, Mp, Kp) || !make_map(&mAl, Al, Mp, Kp) || !make_map(&mBh, Bh, Np, Kp) || !make_map(&mBl, Bl, Np, Kp)) {
+  if (!make_map(&mAh, Ah, Mp, Kp, BM) || !make_map(&mAl, Al, Mp, Kp, BM) || !make_map(&mBh, Bh, Np, Kp, BN) || !make_map(&mBl, Bl, Np, Kp, BN)) {
     AB_CUDA_CHECK(cudaFreeAsync(ws, current_stream()));
     return false;
   }
@@ -282,6 +298,15 @@ bool sgemm_tc(int ta, int tb, int M, int N, int K, float alpha, const float* A, 
                                                                                (int)(Mp / BM), (int)(Np / BN), abort_flag);
   count_launch();
   AB_CUDA_CHECK(cudaGetLastError());
+  if (trace) {
+    cudaEventRecord(ev[3], current_stream());
+    cudaEventSynchronize(ev[3]);
+    float a, b, c;
+    cudaEventElapsedTime(&a, ev[0], ev[1]); cudaEventElapsedTime(&b, ev[1], ev[2]); cudaEventElapsedTime(&c, ev[2], ev[3]);
+    fprintf(stderr, "[sgemm_tc %dx%dx%d] pack A %.3f ms, pack B %.3f ms, mma kernel %.3f ms (%.1f TFLOP/s)\n", M, N, K, a, b, c,
+            2.0 * M * N * K / c / 1e9);
+    for (auto& e : ev) cudaEventDestroy(e);
+  }
   AB_CUDA_CHECK(cudaFreeAsync(ws, current_stream()));
   return true;
 }

@@ -27,7 +27,7 @@ for (M, N, K) in ((128, 128, 32), (128, 128, 512), (256, 384, 96), (257, 131, 51
             resid = n1(C.T.double() - ref) / (max(n1(opA), 1) * max(n1(opB), 1) * max(n1(C0.T.double()), 1) * eps * max(M, N, K))
             flag = "" if resid < 1.0 else "   <-- FAIL"
             if flag or (ta, tb, alpha) == (0, 0, 1.0):
-                print(f"M={M} N={N} K={K} ta={ta} tb={tb} alpha={alpha} beta={beta}: resid {resid:.4f}{flag}", flush=True)
+                print(f"M={M} N={N} K={K} ta={ta} tb={tb} alpha={alpha} beta={beta}: resid {resid:.3e}{flag}", flush=True)
 for n in (4096, 8192, 16384):
     A = torch.rand((n, n), device=dev) - 0.5; B = torch.rand((n, n), device=dev) - 0.5; C = torch.zeros((n, n), device=dev)
     f = lambda: ab.cblas_sgemm(ab.CblasColMajor, ab.CblasNoTrans, ab.CblasNoTrans, n, n, n, 1.0, A, n, B, n, 0.0, C, n)
