@@ -52,6 +52,10 @@ static void gemm_flags(int ta, int ca, int tb, int cb, int M, int N, int K, T al
       return;
   }
   if constexpr (std::is_same<T, float2>::value) {
+    static const bool tc = [] { const char* v = getenv("ATLB200_SGEMM_TC"); return v ? atoi(v) != 0 : true; }();
+    if (tc && (double)M * N * K >= 4194304.0 && M >= 64 && N >= 64 && K >= 32 &&
+        cgemm_tc(ta, p.ca, tb, p.cb, M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, cmode, herk, abort_flag))
+      return;
     if ((double)M * N >= 64.0 * 64.0 && K >= 8 &&
         cgemm_ffma(ta, p.ca, tb, p.cb, M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, cmode, herk, abort_flag))
       return;

@@ -16,4 +16,6 @@ bool cgemm_ffma(int ta, int ca, int tb, int cb, int M, int N, int K, float2 alph
 namespace ab {
 bool sgemm_tc(int ta, int tb, int M, int N, int K, float alpha, const float* A, size_t lda, const float* B, size_t ldb, float beta,
               float* C, size_t ldc, int cmode, const int* abort_flag);
+bool cgemm_tc(int ta, int ca, int tb, int cb, int M, int N, int K, float2 alpha, const float2* A, size_t lda, const float2* B, size_t ldb,
+              float2 beta, float2* C, size_t ldc, int cmode, int herk, const int* abort_flag);
 }

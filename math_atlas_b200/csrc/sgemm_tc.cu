@@ -132,18 +132,80 @@ __global__ void __launch_bounds__(256) split_pack_kernel(int R, int K, int Rp, i
   }
 }
 
+__device__ __forceinline__ void split_store(float* __restrict__ Ph, float* __restrict__ Pl, size_t o, float a) {
+  uint32_t hb, lb;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hb) : "f"(a));
+  const float hi = __uint_as_float(hb);
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(lb) : "f"(a - hi));
+  Ph[o] = hi;
+  Pl[o] = __uint_as_float(lb);
+}
+// complex cm2am.  X is float2; op(X)(r,k) = X[r + k*ld] (kcontig=0) or X[k + r*ld] (kcontig=1), conjugated if cj.
+// KBh = Kp/32 k blocks hold the first half of the doubled K, the next KBh the second half.
+//   isB = 0: packed row r:  [ re(r,k) | im(r,k) ]                                   (Rp rows)
+//   isB = 1: complex column n -> packed rows 256*(n/128) + n%128 ("re" row): [ re(k,n) | -im(k,n) ]
+//                                        and 256*(n/128) + 128 + n%128 ("im" row): [ im(k,n) |  re(k,n) ]
+__global__ void __launch_bounds__(256) split_pack_cplx_kernel(int R, int K, int Rp, int Kp, const float2* __restrict__ X, size_t ld,
+                                                              int kcontig, int cj, int isB, float* __restrict__ Ph, float* __restrict__ Pl) {
+  __shared__ float2 t[32][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int r0 = blockIdx.y * 32, k0 = blockIdx.x * 32, KBh = Kp / 32;
+  const float2 zero = make_float2(0.f, 0.f);
+  if (kcontig) {
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+      const int r = r0 + ty + 8 * i, k = k0 + tx;
+      t[ty + 8 * i][tx] = (r < R && k < K) ? X[(size_t)k + (size_t)r * ld] : zero;
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+      const int k = k0 + ty + 8 * i, r = r0 + tx;
+      t[tx][ty + 8 * i] = (r < R && k < K) ? X[(size_t)r + (size_t)k * ld] : zero;
+    }
+  }
+  __syncthreads();
+  const size_t prow = isB ? 2 * (size_t)Rp : (size_t)Rp;      // packed rows per k block
+#pragma unroll
+  for (int i = 0; i < 4; i++) {
+    const int r = r0 + ty + 8 * i;
+    float2 a = t[ty + 8 * i][tx];
+    if (cj) a.y = -a.y;
+    const size_t kb1 = blockIdx.x, kb2 = blockIdx.x + KBh;
+    if (!isB) {
+      split_store(Ph, Pl, (kb1 * prow + r) * 32 + tx, a.x);
+      split_store(Ph, Pl, (kb2 * prow + r) * 32 + tx, a.y);
+    } else {
+      const size_t rr = 256 * (size_t)(r / 128) + (r % 128), ri = rr + 128;
+      split_store(Ph, Pl, (kb1 * prow + rr) * 32 + tx, a.x);
+      split_store(Ph, Pl, (kb2 * prow + rr) * 32 + tx, -a.y);
+      split_store(Ph, Pl, (kb1 * prow + ri) * 32 + tx, a.y);
+      split_store(Ph, Pl, (kb2 * prow + ri) * 32 + tx, a.x);
+    }
+  }
+}
+
 // ---------------------------------------------------------------- the tensor-core kernel
+// CPLX: the same pipeline computes a complex product as the real one of doubled size
+//     [C_re | C_im] = [A_re | A_im] * [[B_re, B_im], [-B_im, B_re]]       (M x 2K times 2K x 2N, 8MNK flop)
+// on panels the complex copy kernel lays out so that a 256-row B block holds the "re" rows and the "im" rows
+// of the same 128 complex columns: accumulator columns 0..127 are Re(C), 128..255 are Im(C), and the
+// epilogue writes them interleaved.  M, N count complex elements then, C is float2 and alpha/beta are complex.
+template <bool CPLX>
 __global__ void __launch_bounds__(THREADS, 1)
 sgemm_tc_kernel(const __grid_constant__ CUtensorMap mAh, const __grid_constant__ CUtensorMap mAl,
                 const __grid_constant__ CUtensorMap mBh, const __grid_constant__ CUtensorMap mBl, float* __restrict__ C, size_t ldc, int M,
-                int N, int KB, float alpha, float beta, int cmode, int tiles_m, int tiles_n, const int* __restrict__ abort_flag) {
+                int N, int KB, float alpha, float beta, int cmode, int tiles_m, int tiles_n, const int* __restrict__ abort_flag,
+                float alpha_im, float beta_im, int herk) {
   if (abort_flag && *abort_flag) return;
+  constexpr int TN = CPLX ? BN / 2 : BN;               // output columns per tile (complex: 128)
   // grouped rasterisation (same map as dgemm_tma.cu)
   const int in_group = GROUP_M * tiles_n;
   const int first_m = ((int)blockIdx.x / in_group) * GROUP_M;
   const int gsz = min(tiles_m - first_m, GROUP_M);
-  const int m0 = (first_m + ((int)blockIdx.x % in_group) % gsz) * BM, n0 = (((int)blockIdx.x % in_group) / gsz) * BN;
-  if (cmode == C_UPPER && m0 > n0 + BN - 1) return;
+  const int tn = ((int)blockIdx.x % in_group) / gsz;
+  const int m0 = (first_m + ((int)blockIdx.x % in_group) % gsz) * BM, n0 = tn * TN;
+  if (cmode == C_UPPER && m0 > n0 + TN - 1) return;
   if (cmode == C_LOWER && n0 > m0 + BM - 1) return;
 
   extern __shared__ uint8_t smem_raw[];
@@ -175,8 +237,8 @@ sgemm_tc_kernel(const __grid_constant__ CUtensorMap mAh, const __grid_constant__
         mbar_expect_tx(full, STAGE_BYTES);
         tma_load_3d(dst, &mAh, 0, m0, kb, full);
         tma_load_3d(dst + A_TILE_BYTES, &mAl, 0, m0, kb, full);
-        tma_load_3d(dst + 2 * A_TILE_BYTES, &mBh, 0, n0, kb, full);
-        tma_load_3d(dst + 2 * A_TILE_BYTES + B_TILE_BYTES, &mBl, 0, n0, kb, full);
+        tma_load_3d(dst + 2 * A_TILE_BYTES, &mBh, 0, tn * BN, kb, full);      // packed B rows of this tile
+        tma_load_3d(dst + 2 * A_TILE_BYTES + B_TILE_BYTES, &mBl, 0, tn * BN, kb, full);
       }
     }
   } else if (warp == 1) {
@@ -204,22 +266,48 @@ sgemm_tc_kernel(const __grid_constant__ CUtensorMap mAh, const __grid_constant__
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const int q = warp & 3;
     const int m = m0 + q * 32 + lane;
-    const bool beta0 = (beta == 0.f);
+    if constexpr (!CPLX) {
+      const bool beta0 = (beta == 0.f);
 #pragma unroll 1
-    for (int c0 = 0; c0 < BN; c0 += 32) {
-      uint32_t r[32];
-      tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, r);
-      if (m < M) {
+      for (int c0 = 0; c0 < BN; c0 += 32) {
+        uint32_t r[32];
+        tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, r);
+        if (m < M) {
 #pragma unroll
-        for (int j = 0; j < 32; j++) {
-          const int n = n0 + c0 + j;
-          if (n >= N) continue;
-          if (cmode == C_UPPER && m > n) continue;
-          if (cmode == C_LOWER && m < n) continue;
-          float* c = C + (size_t)m + (size_t)n * ldc;
-          float v = alpha * __uint_as_float(r[j]);
-          if (!beta0) v += beta * *c;
-          *c = v;
+          for (int j = 0; j < 32; j++) {
+            const int n = n0 + c0 + j;
+            if (n >= N) continue;
+            if (cmode == C_UPPER && m > n) continue;
+            if (cmode == C_LOWER && m < n) continue;
+            float* c = C + (size_t)m + (size_t)n * ldc;
+            float v = alpha * __uint_as_float(r[j]);
+            if (!beta0) v += beta * *c;
+            *c = v;
+          }
+        }
+      }
+    } else {
+      const bool beta0 = (beta == 0.f && beta_im == 0.f);
+      float2* Cz = reinterpret_cast<float2*>(C);
+#pragma unroll 1
+      for (int c0 = 0; c0 < TN; c0 += 32) {
+        uint32_t re[32], im[32];
+        tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, re);
+        tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(TN + c0), im);
+        if (m < M) {
+#pragma unroll
+          for (int j = 0; j < 32; j++) {
+            const int n = n0 + c0 + j;
+            if (n >= N) continue;
+            if (cmode == C_UPPER && m > n) continue;
+            if (cmode == C_LOWER && m < n) continue;
+            float2* c = Cz + (size_t)m + (size_t)n * ldc;
+            const float xr = __uint_as_float(re[j]), xi = __uint_as_float(im[j]);
+            float2 v = make_float2(alpha * xr - alpha_im * xi, alpha * xi + alpha_im * xr);
+            if (!beta0) { const float2 o = *c; v.x += beta * o.x - beta_im * o.y; v.y += beta * o.y + beta_im * o.x; }
+            if (herk && m == n) v.y = 0.f;
+            *c = v;
+          }
         }
       }
     }
@@ -260,6 +348,11 @@ bool make_map(CUtensorMap* tm, const float* ptr, size_t Rp, size_t Kp, int box_r
 
 }  // namespace
 
+static bool ws_budget_ok(size_t bytes) {
+  static const size_t budget = [] { const char* v = getenv("ATLB200_SGEMM_TC_WS_GB"); return (size_t)(v ? atof(v) : 12.0) << 30; }();
+  return bytes <= budget;
+}
+
 // op(A) is M x K, op(B) is K x N.  Returns false (nothing done) when the packed panels would not fit
 // the workspace budget; the caller then uses the FFMA kernel.
 bool sgemm_tc(int ta, int tb, int M, int N, int K, float alpha, const float* A, size_t lda, const float* B, size_t ldb, float beta,
@@ -267,8 +360,7 @@ bool sgemm_tc(int ta, int tb, int M, int N, int K, float alpha, const float* A, 
   if (M <= 0 || N <= 0 || K <= 0) return false;
   const size_t Mp = ((size_t)M + BM - 1) / BM * BM, Np = ((size_t)N + BN - 1) / BN * BN, Kp = ((size_t)K + BK - 1) / BK * BK;
   const size_t bytes = 2 * sizeof(float) * (Mp + Np) * Kp;
-  static const size_t budget = [] { const char* v = getenv("ATLB200_SGEMM_TC_WS_GB"); return (size_t)(v ? atof(v) : 12.0) << 30; }();
-  if (bytes > budget) return false;
+  if (!ws_budget_ok(bytes)) return false;
   const long long tiles = (long long)(Mp / BM) * (long long)(Np / BN);
   if (tiles > 0x7fffffffLL) return false;
   // stream-ordered pool allocation: the look-ahead factorisations issue GEMMs from two streams
@@ -278,35 +370,56 @@ bool sgemm_tc(int ta, int tb, int M, int N, int K, float alpha, const float* A, 
   float *Ah = ws, *Al = Ah + Mp * Kp, *Bh = Al + Mp * Kp, *Bl = Bh + Np * Kp;
   // cm2am: op(A)(m,k) = A[m + k*lda] (NoTrans) or A[k + m*lda] (Trans: K contiguous); op(B)(k,n): rows of the packed
   // panel are n, so B NoTrans (B[k + n*ldb]) is the K-contiguous case
-  static const bool trace = getenv("ATLB200_SGEMM_TC_TRACE") != nullptr;
-  cudaEvent_t ev[4];
-  if (trace) { for (auto& e : ev) cudaEventCreate(&e); cudaEventRecord(ev[0], current_stream()); }
   split_pack_kernel<<<dim3((unsigned)(Kp / 32), (unsigned)(Mp / 32)), 256, 0, current_stream()>>>(M, K, (int)Mp, (int)Kp, A, lda, ta ? 1 : 0, Ah, Al);
-  if (trace) cudaEventRecord(ev[1], current_stream());
   split_pack_kernel<<<dim3((unsigned)(Kp / 32), (unsigned)(Np / 32)), 256, 0, current_stream()>>>(N, K, (int)Np, (int)Kp, B, ldb, tb ? 0 : 1, Bh, Bl);
   count_launch(2);
   AB_CUDA_CHECK(cudaGetLastError());
-  if (trace) cudaEventRecord(ev[2], current_stream());
   CUtensorMap mAh, mAl, mBh, mBl;
   if (!make_map(&mAh, Ah, Mp, Kp, BM) || !make_map(&mAl, Al, Mp, Kp, BM) || !make_map(&mBh, Bh, Np, Kp, BN) || !make_map(&mBl, Bl, Np, Kp, BN)) {
     AB_CUDA_CHECK(cudaFreeAsync(ws, current_stream()));
     return false;
   }
   static bool attr = false;
-  if (!attr) { AB_CUDA_CHECK(cudaFuncSetAttribute(sgemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES)); attr = true; }
-  sgemm_tc_kernel<<<(unsigned)tiles, THREADS, SMEM_BYTES, current_stream()>>>(mAh, mAl, mBh, mBl, C, ldc, M, N, (int)(Kp / BK), alpha, beta, cmode,
-                                                                               (int)(Mp / BM), (int)(Np / BN), abort_flag);
+  if (!attr) { AB_CUDA_CHECK(cudaFuncSetAttribute(sgemm_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES)); attr = true; }
+  sgemm_tc_kernel<false><<<(unsigned)tiles, THREADS, SMEM_BYTES, current_stream()>>>(mAh, mAl, mBh, mBl, C, ldc, M, N, (int)(Kp / BK), alpha, beta,
+                                                                                      cmode, (int)(Mp / BM), (int)(Np / BN), abort_flag, 0.f, 0.f, 0);
   count_launch();
   AB_CUDA_CHECK(cudaGetLastError());
-  if (trace) {
-    cudaEventRecord(ev[3], current_stream());
-    cudaEventSynchronize(ev[3]);
-    float a, b, c;
-    cudaEventElapsedTime(&a, ev[0], ev[1]); cudaEventElapsedTime(&b, ev[1], ev[2]); cudaEventElapsedTime(&c, ev[2], ev[3]);
-    fprintf(stderr, "[sgemm_tc %dx%dx%d] pack A %.3f ms, pack B %.3f ms, mma kernel %.3f ms (%.1f TFLOP/s)\n", M, N, K, a, b, c,
-            2.0 * M * N * K / c / 1e9);
-    for (auto& e : ev) cudaEventDestroy(e);
+  AB_CUDA_CHECK(cudaFreeAsync(ws, current_stream()));
+  return true;
+}
+
+// complex float on the same pipeline (see sgemm_tc_kernel<true>): ta/tb transposed, ca/cb conjugated
+bool cgemm_tc(int ta, int ca, int tb, int cb, int M, int N, int K, float2 alpha, const float2* A, size_t lda, const float2* B, size_t ldb,
+              float2 beta, float2* C, size_t ldc, int cmode, int herk, const int* abort_flag) {
+  if (M <= 0 || N <= 0 || K <= 0) return false;
+  constexpr int TNc = BN / 2;                                                   // complex columns per tile
+  const size_t Mp = ((size_t)M + BM - 1) / BM * BM, Np = ((size_t)N + TNc - 1) / TNc * TNc, Kp = ((size_t)K + BK - 1) / BK * BK;
+  const size_t K2 = 2 * Kp;                                                     // doubled inner dimension
+  const size_t bytes = 2 * sizeof(float) * (Mp + 2 * Np) * K2;
+  if (!ws_budget_ok(bytes)) return false;
+  const long long tiles = (long long)(Mp / BM) * (long long)(Np / TNc);
+  if (tiles > 0x7fffffffLL) return false;
+  float* ws = nullptr;
+  keep_pool_cached();
+  AB_CUDA_CHECK(cudaMallocAsync(&ws, bytes, current_stream()));
+  float *Ah = ws, *Al = Ah + Mp * K2, *Bh = Al + Mp * K2, *Bl = Bh + 2 * Np * K2;
+  split_pack_cplx_kernel<<<dim3((unsigned)(Kp / 32), (unsigned)(Mp / 32)), 256, 0, current_stream()>>>(M, K, (int)Mp, (int)Kp, A, lda, ta ? 1 : 0, ca, 0, Ah, Al);
+  split_pack_cplx_kernel<<<dim3((unsigned)(Kp / 32), (unsigned)(Np / 32)), 256, 0, current_stream()>>>(N, K, (int)Np, (int)Kp, B, ldb, tb ? 0 : 1, cb, 1, Bh, Bl);
+  count_launch(2);
+  AB_CUDA_CHECK(cudaGetLastError());
+  CUtensorMap mAh, mAl, mBh, mBl;
+  if (!make_map(&mAh, Ah, Mp, K2, BM) || !make_map(&mAl, Al, Mp, K2, BM) || !make_map(&mBh, Bh, 2 * Np, K2, BN) || !make_map(&mBl, Bl, 2 * Np, K2, BN)) {
+    AB_CUDA_CHECK(cudaFreeAsync(ws, current_stream()));
+    return false;
   }
+  static bool attr = false;
+  if (!attr) { AB_CUDA_CHECK(cudaFuncSetAttribute(sgemm_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES)); attr = true; }
+  sgemm_tc_kernel<true><<<(unsigned)tiles, THREADS, SMEM_BYTES, current_stream()>>>(mAh, mAl, mBh, mBl, reinterpret_cast<float*>(C), ldc, M, N,
+                                                                                     (int)(K2 / BK), alpha.x, beta.x, cmode, (int)(Mp / BM),
+                                                                                     (int)(Np / TNc), abort_flag, alpha.y, beta.y, herk);
+  count_launch();
+  AB_CUDA_CHECK(cudaGetLastError());
   AB_CUDA_CHECK(cudaFreeAsync(ws, current_stream()));
   return true;
 }

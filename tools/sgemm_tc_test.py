@@ -38,3 +38,13 @@ for n in (4096, 8192, 16384):
     e1.record(); torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / 3
     print(f"sgemm n={n}: {ms:.2f} ms  {2.0 * n ** 3 / ms / 1e9:.1f} TFLOP/s", flush=True)
+for n in (4096, 8192):
+    A = torch.rand((n, n, 2), device=dev) - 0.5; B = torch.rand((n, n, 2), device=dev) - 0.5; C = torch.zeros((n, n, 2), device=dev)
+    f = lambda: ab.cblas_cgemm(ab.CblasColMajor, ab.CblasNoTrans, ab.CblasNoTrans, n, n, n, 1.0, A, n, B, n, 0.0, C, n)
+    f(); torch.cuda.synchronize()
+    e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(3): f()
+    e1.record(); torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / 3
+    print(f"cgemm n={n}: {ms:.2f} ms  {8.0 * n ** 3 / ms / 1e9:.1f} TFLOP/s", flush=True)
