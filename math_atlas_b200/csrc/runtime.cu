@@ -65,6 +65,14 @@ void free_workspace() {
   Slots& s = g_slots;
   for (int i = 0; i < Slots::N; i++)
     if (s.ptr[i]) { cudaFree(s.ptr[i]); s.ptr[i] = nullptr; s.size[i] = 0; }
+  // ... and what the stream-ordered pool has cached (staged host operands, packed tensor-core panels)
+  int dev = 0;
+  cudaMemPool_t pool;
+  if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+    (void)cudaDeviceSynchronize();
+    (void)cudaMemPoolTrimTo(pool, 0);
+  }
+  (void)cudaGetLastError();
 }
 
 }  // namespace ab

@@ -349,7 +349,7 @@ bool make_map(CUtensorMap* tm, const float* ptr, size_t Rp, size_t Kp, int box_r
 }  // namespace
 
 static bool ws_budget_ok(size_t bytes) {
-  static const size_t budget = [] { const char* v = getenv("ATLB200_SGEMM_TC_WS_GB"); return (size_t)(v ? atof(v) : 12.0) << 30; }();
+  static const size_t budget = [] { const char* v = getenv("ATLB200_SGEMM_TC_WS_GB"); return (size_t)((v ? atof(v) : 20.0) * 1073741824.0); }();
   return bytes <= budget;
 }
 
@@ -360,7 +360,24 @@ bool sgemm_tc(int ta, int tb, int M, int N, int K, float alpha, const float* A, 
   if (M <= 0 || N <= 0 || K <= 0) return false;
   const size_t Mp = ((size_t)M + BM - 1) / BM * BM, Np = ((size_t)N + BN - 1) / BN * BN, Kp = ((size_t)K + BK - 1) / BK * BK;
   const size_t bytes = 2 * sizeof(float) * (Mp + Np) * Kp;
-  if (!ws_budget_ok(bytes)) return false;
+  if (!ws_budget_ok(bytes)) {
+    // packed panels over the budget: halve the larger output dimension (the copy is O(N^2), repeating it is cheap)
+    if (cmode != C_FULL) return false;
+    if (N >= M && N >= 2 * BN) {
+      const int n1 = (N / 2 + BN - 1) / BN * BN;
+      const float* B2 = tb ? B + n1 : B + (size_t)n1 * ldb;
+      return sgemm_tc(ta, tb, M, n1, K, alpha, A, lda, B, ldb, beta, C, ldc, cmode, abort_flag) &&
+             sgemm_tc(ta, tb, M, N - n1, K, alpha, A, lda, B2, ldb, beta, C + (size_t)n1 * ldc, ldc, cmode, abort_flag);
+    }
+    if (M >= 2 * BM) {
+      const int m1 = (M / 2 + BM - 1) / BM * BM;
+      const float* A2 = ta ? A + (size_t)m1 * lda : A + m1;
+      return sgemm_tc(ta, tb, m1, N, K, alpha, A, lda, B, ldb, beta, C, ldc, cmode, abort_flag) &&
+             sgemm_tc(ta, tb, M - m1, N, K, alpha, A2, lda, B, ldb, beta, C + m1, ldc, cmode, abort_flag);
+    }
+    // a piece that cannot be halved any further (huge K): the FFMA kernel finishes it, so that a split is all-or-nothing
+    return sgemm_ffma(ta, tb, M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, cmode, abort_flag);
+  }
   const long long tiles = (long long)(Mp / BM) * (long long)(Np / BN);
   if (tiles > 0x7fffffffLL) return false;
   // stream-ordered pool allocation: the look-ahead factorisations issue GEMMs from two streams
@@ -397,7 +414,22 @@ bool cgemm_tc(int ta, int ca, int tb, int cb, int M, int N, int K, float2 alpha,
   const size_t Mp = ((size_t)M + BM - 1) / BM * BM, Np = ((size_t)N + TNc - 1) / TNc * TNc, Kp = ((size_t)K + BK - 1) / BK * BK;
   const size_t K2 = 2 * Kp;                                                     // doubled inner dimension
   const size_t bytes = 2 * sizeof(float) * (Mp + 2 * Np) * K2;
-  if (!ws_budget_ok(bytes)) return false;
+  if (!ws_budget_ok(bytes)) {
+    if (cmode != C_FULL) return false;
+    if (N >= M && N >= 2 * TNc) {
+      const int n1 = (N / 2 + TNc - 1) / TNc * TNc;
+      const float2* B2 = tb ? B + n1 : B + (size_t)n1 * ldb;
+      return cgemm_tc(ta, ca, tb, cb, M, n1, K, alpha, A, lda, B, ldb, beta, C, ldc, cmode, herk, abort_flag) &&
+             cgemm_tc(ta, ca, tb, cb, M, N - n1, K, alpha, A, lda, B2, ldb, beta, C + (size_t)n1 * ldc, ldc, cmode, herk, abort_flag);
+    }
+    if (M >= 2 * BM) {
+      const int m1 = (M / 2 + BM - 1) / BM * BM;
+      const float2* A2 = ta ? A + (size_t)m1 * lda : A + m1;
+      return cgemm_tc(ta, ca, tb, cb, m1, N, K, alpha, A, lda, B, ldb, beta, C, ldc, cmode, herk, abort_flag) &&
+             cgemm_tc(ta, ca, tb, cb, M - m1, N, K, alpha, A2, lda, B, ldb, beta, C + m1, ldc, cmode, herk, abort_flag);
+    }
+    return cgemm_ffma(ta, ca, tb, cb, M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, cmode, herk, abort_flag);
+  }
   const long long tiles = (long long)(Mp / BM) * (long long)(Np / TNc);
   if (tiles > 0x7fffffffLL) return false;
   float* ws = nullptr;
