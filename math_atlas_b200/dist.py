@@ -12,6 +12,8 @@ update by look-ahead).  Every GPU reaches every peer at full NVLink bandwidth, s
 distribution costs no more than a 2-D one for the broadcast.
 
   pgemm   : C slab <- alpha*A*B slab + beta*C slab, no collective (B and C split by columns; never split K)
+  psyrk   : the column slab [c0, c1) of one triangle of C <- alpha*A*A^T + beta*C: one SYRK + one GEMM, no collective
+  ptrsm / ptrmm : Side=Left, B split by columns (independent right-hand sides), the triangle replicated, no collective
   pgetrf  : right-looking blocked LU with partial pivoting, look-ahead depth 1
   ppotrf  : right-looking blocked Cholesky (lower), look-ahead depth 1
 
@@ -127,6 +129,10 @@ class CudaOps:
         s = self._S(self.pre, alpha)
         getattr(self.L, f"cblas_{self.pre}trsm")(CblasColMajor, side, uplo, trans, diag, M, N, s.arg, a, lda, b, ldb)
 
+    def trmm(self, side, uplo, trans, diag, M, N, alpha, a, lda, b, ldb):
+        s = self._S(self.pre, alpha)
+        getattr(self.L, f"cblas_{self.pre}trmm")(CblasColMajor, side, uplo, trans, diag, M, N, s.arg, a, lda, b, ldb)
+
     def gemm(self, ta, tb, M, N, K, alpha, a, lda, b, ldb, beta, c, ldc):
         s, t = self._S(self.pre, alpha), self._S(self.pre, beta)
         getattr(self.L, f"cblas_{self.pre}gemm")(CblasColMajor, ta, tb, M, N, K, s.arg, a, lda, b, ldb, t.arg, c, ldc)
@@ -153,6 +159,35 @@ def pgemm(ops, M, N_local, K, alpha, A, lda, B_loc, ldb, beta, C_loc, ldc):
     """This rank's column slab of C <- alpha*A*B + beta*C.  No collective: the output is partitioned
     by columns and K is never split (reference decomposition ATL_thrdecompMM, atlas-thr.base:5197)."""
     ops.gemm(CblasNoTrans, CblasNoTrans, M, N_local, K, alpha, A.data_ptr(), lda, B_loc.data_ptr(), ldb, beta, C_loc.data_ptr(), ldc)
+
+
+def psyrk(ops, uplo, N, K, c0, c1, alpha, A, lda, beta, C_loc, ldc):
+    """Columns [c0, c1) of the `uplo` triangle of C <- alpha*A*A^T + beta*C (A is N x K, NoTrans; A*A^H for c/z).
+    C_loc holds those columns with all N rows (leading dimension ldc).  The diagonal block is a SYRK,
+    the rectangle above (Upper) or below (Lower) it a GEMM with the matching rows of A: no collective
+    (the reference's ATL_tsyrk splits the triangle the same way, atlas-thr.base:7781)."""
+    w = c1 - c0
+    if w <= 0:
+        return
+    es = C_loc.element_size()
+    Ablk = A.data_ptr() + c0 * es                      # rows c0.. of A
+    ops.syrk(uplo, CblasNoTrans, w, K, alpha, Ablk, lda, beta, C_loc.data_ptr() + c0 * es, ldc)
+    tr = CblasConjTrans if ops.pre in "cz" else CblasTrans
+    if uplo == CblasLower and N - c1 > 0:
+        ops.gemm(CblasNoTrans, tr, N - c1, w, K, alpha, A.data_ptr() + c1 * es, lda, Ablk, lda, beta, C_loc.data_ptr() + c1 * es, ldc)
+    if uplo == CblasUpper and c0 > 0:
+        ops.gemm(CblasNoTrans, tr, c0, w, K, alpha, A.data_ptr(), lda, Ablk, lda, beta, C_loc.data_ptr(), ldc)
+
+
+def ptrsm(ops, uplo, trans, diag, M, N_local, alpha, A, lda, B_loc, ldb):
+    """This rank's right-hand sides: B_loc <- alpha * inv(op(A)) * B_loc (Side=Left).  Right-hand sides are
+    independent, the triangle is replicated: no collective."""
+    ops.trsm(CblasLeft, uplo, trans, diag, M, N_local, alpha, A.data_ptr(), lda, B_loc.data_ptr(), ldb)
+
+
+def ptrmm(ops, uplo, trans, diag, M, N_local, alpha, A, lda, B_loc, ldb):
+    """This rank's columns: B_loc <- alpha * op(A) * B_loc (Side=Left), no collective."""
+    ops.trmm(CblasLeft, uplo, trans, diag, M, N_local, alpha, A.data_ptr(), lda, B_loc.data_ptr(), ldb)
 
 
 def pgetrf(pre, M, lay, A_loc, ld, ops, group=None, lookahead=True):

@@ -40,6 +40,10 @@ class OracleOps:
         k, p = self._s(alpha)
         getattr(self.L, f"orc_{self.pre}trsm")(side, uplo, trans, diag, M, N, p, C.c_void_p(a), lda, C.c_void_p(b), ldb)
 
+    def trmm(self, side, uplo, trans, diag, M, N, alpha, a, lda, b, ldb):
+        k, p = self._s(alpha)
+        getattr(self.L, f"orc_{self.pre}trmm")(side, uplo, trans, diag, M, N, p, C.c_void_p(a), lda, C.c_void_p(b), ldb)
+
     def gemm(self, ta, tb, M, N, K, alpha, a, lda, b, ldb, beta, c, ldc):
         k1, p1 = self._s(alpha); k2, p2 = self._s(beta)
         getattr(self.L, f"orc_{self.pre}gemm")(ta, tb, M, N, K, p1, C.c_void_p(a), lda, C.c_void_p(b), ldb, p2, C.c_void_p(c), ldc)
@@ -122,8 +126,45 @@ def _one_case(rank, world, case, q):
                 q.put((case, np.array_equal(got, want)))
 
 
+        elif kind in ("syrk", "trsm", "trmm"):
+            # column slabs [lo, hi) per rank, no collective; the assembled result must equal the one-call oracle result
+            K = M
+            lo, hi = rank * (N // world), (rank + 1) * (N // world) if rank < world - 1 else N
+            if kind == "syrk":
+                A = o.gegen(pre, N, K, N, 5); C0 = o.gegen(pre, N, N, N, 6)
+                At = torch.from_numpy(np.ascontiguousarray(A.T)); Cl = torch.from_numpy(C0[:, lo:hi].T.copy())
+                al, be = (-1.1, 0.7)
+                for uplo in (orc.Upper, orc.Lower):
+                    Cl = torch.from_numpy(C0[:, lo:hi].T.copy())
+                    abd.psyrk(ops, uplo, N, K, lo, hi, al, At, N, be, Cl, N)
+                    parts = [None] * world
+                    dist.all_gather_object(parts, Cl)
+                    if rank == 0:
+                        got = np.concatenate([p.numpy().T for p in parts], axis=1)
+                        want = C0.copy(order="F")
+                        (o.herk if orc.CPLX[pre] else o.syrk)(pre, uplo, orc.NoTrans, N, K, al, A, be, want)
+                        tri = np.triu_indices(N) if uplo == orc.Upper else np.tril_indices(N)
+                        other = np.tril_indices(N, -1) if uplo == orc.Upper else np.triu_indices(N, 1)
+                        okk = (np.max(np.abs(got[tri] - want[tri])) <= 64 * orc.eps_of(pre) * K and np.array_equal(got[other], C0[other]))
+                        if uplo == orc.Upper: ok = okk
+                        else: q.put((case, ok and okk))
+            else:
+                A = o.gegen(pre, M, M, M, 7); o.trddom(pre, orc.Lower, M, A); B0 = o.gegen(pre, M, N, M, 8)
+                At = torch.from_numpy(np.ascontiguousarray(A.T)); Bl = torch.from_numpy(B0[:, lo:hi].T.copy())
+                fn = abd.ptrsm if kind == "trsm" else abd.ptrmm
+                fn(ops, orc.Lower, orc.NoTrans, orc.NonUnit, M, hi - lo, 1.0, At, M, Bl, M)
+                parts = [None] * world
+                dist.all_gather_object(parts, Bl)
+                if rank == 0:
+                    got = np.concatenate([p.numpy().T for p in parts], axis=1)
+                    want = B0.copy(order="F")
+                    (o.trsm if kind == "trsm" else o.trmm)(pre, orc.Left, orc.Lower, orc.NoTrans, orc.NonUnit, M, N, 1.0, A, want)
+                    q.put((case, np.array_equal(got, want)))
+
+
 CASES = [("d", "getrf", 150, 150, 32), ("d", "getrf", 200, 96, 32), ("s", "getrf", 97, 97, 16), ("z", "getrf", 70, 70, 16),
-         ("d", "potrf", 0, 130, 32), ("z", "potrf", 0, 75, 16), ("d", "potrf_bad", 50, 96, 32), ("d", "gemm", 40, 37, 0)]
+         ("d", "potrf", 0, 130, 32), ("z", "potrf", 0, 75, 16), ("d", "potrf_bad", 50, 96, 32), ("d", "gemm", 40, 37, 0),
+         ("d", "syrk", 33, 47, 0), ("z", "syrk", 20, 31, 0), ("d", "trsm", 45, 38, 0), ("c", "trmm", 30, 29, 0)]
 
 
 @pytest.mark.parametrize("world", [2, 3])
