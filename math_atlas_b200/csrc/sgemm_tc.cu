@@ -12,7 +12,7 @@
 // canonicalises the four transpose cases, and the compute kernel (ammkern, :577) only ever sees
 // one layout.  The copy is O(N^2) HBM traffic against O(N^3) tensor work.
 //
-// Compute kernel: one CTA per 128x256 tile (operand bytes per flop 25 % below 128x128: the kernel is
+// Compute kernel, single-CTA form (the default is the CTA-pair form further down): one CTA per 128x256 tile (operand bytes per flop 25 % below 128x128: the kernel is
 // bound by the L2 -> shared-memory feed, not by the tensor pipe), 192 threads:
 //   warp 0   TMA producer: per k block of 32 the four tiles A_hi, A_lo (128 rows), B_hi, B_lo (256 rows) of
 //            128-byte rows, SWIZZLE_128B = the canonical K-major UMMA layout; 2-stage ring of 96 KB
@@ -186,6 +186,59 @@ __global__ void __launch_bounds__(256) split_pack_cplx_kernel(int R, int K, int 
 }
 
 // ---------------------------------------------------------------- the tensor-core kernel
+// C = alpha*acc + beta*C for the 32 tile rows of TMEM lane quarter q (rows m0 + 32q + lane), all TN output columns
+template <bool CPLX>
+__device__ __forceinline__ void tc_epilogue(uint32_t tmem, int q, int lane, int m0, int n0, int M, int N, float* __restrict__ C, size_t ldc,
+                                            float alpha, float beta, float alpha_im, float beta_im, int cmode, int herk) {
+  constexpr int TN = CPLX ? BN / 2 : BN;
+  const int m = m0 + q * 32 + lane;
+  if constexpr (!CPLX) {
+    const bool beta0 = (beta == 0.f);
+#pragma unroll 1
+    for (int c0 = 0; c0 < BN; c0 += 32) {
+      uint32_t r[32];
+      tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, r);
+      if (m < M) {
+#pragma unroll
+        for (int j = 0; j < 32; j++) {
+          const int n = n0 + c0 + j;
+          if (n >= N) continue;
+          if (cmode == C_UPPER && m > n) continue;
+          if (cmode == C_LOWER && m < n) continue;
+          float* c = C + (size_t)m + (size_t)n * ldc;
+          float v = alpha * __uint_as_float(r[j]);
+          if (!beta0) v += beta * *c;
+          *c = v;
+        }
+      }
+    }
+  } else {
+    const bool beta0 = (beta == 0.f && beta_im == 0.f);
+    float2* Cz = reinterpret_cast<float2*>(C);
+#pragma unroll 1
+    for (int c0 = 0; c0 < TN; c0 += 32) {
+      uint32_t re[32], im[32];
+      tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, re);
+      tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(TN + c0), im);
+      if (m < M) {
+#pragma unroll
+        for (int j = 0; j < 32; j++) {
+          const int n = n0 + c0 + j;
+          if (n >= N) continue;
+          if (cmode == C_UPPER && m > n) continue;
+          if (cmode == C_LOWER && m < n) continue;
+          float2* c = Cz + (size_t)m + (size_t)n * ldc;
+          const float xr = __uint_as_float(re[j]), xi = __uint_as_float(im[j]);
+          float2 v = make_float2(alpha * xr - alpha_im * xi, alpha * xi + alpha_im * xr);
+          if (!beta0) { const float2 o = *c; v.x += beta * o.x - beta_im * o.y; v.y += beta * o.y + beta_im * o.x; }
+          if (herk && m == n) v.y = 0.f;
+          *c = v;
+        }
+      }
+    }
+  }
+  }
+
 // CPLX: the same pipeline computes a complex product as the real one of doubled size
 //     [C_re | C_im] = [A_re | A_im] * [[B_re, B_im], [-B_im, B_re]]       (M x 2K times 2K x 2N, 8MNK flop)
 // on panels the complex copy kernel lays out so that a 256-row B block holds the "re" rows and the "im" rows
@@ -265,57 +318,134 @@ sgemm_tc_kernel(const __grid_constant__ CUtensorMap mAh, const __grid_constant__
     mbar_wait(bars + 8 * (2 * STAGES), 0);
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const int q = warp & 3;
-    const int m = m0 + q * 32 + lane;
-    if constexpr (!CPLX) {
-      const bool beta0 = (beta == 0.f);
-#pragma unroll 1
-      for (int c0 = 0; c0 < BN; c0 += 32) {
-        uint32_t r[32];
-        tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, r);
-        if (m < M) {
-#pragma unroll
-          for (int j = 0; j < 32; j++) {
-            const int n = n0 + c0 + j;
-            if (n >= N) continue;
-            if (cmode == C_UPPER && m > n) continue;
-            if (cmode == C_LOWER && m < n) continue;
-            float* c = C + (size_t)m + (size_t)n * ldc;
-            float v = alpha * __uint_as_float(r[j]);
-            if (!beta0) v += beta * *c;
-            *c = v;
-          }
-        }
-      }
-    } else {
-      const bool beta0 = (beta == 0.f && beta_im == 0.f);
-      float2* Cz = reinterpret_cast<float2*>(C);
-#pragma unroll 1
-      for (int c0 = 0; c0 < TN; c0 += 32) {
-        uint32_t re[32], im[32];
-        tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, re);
-        tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(TN + c0), im);
-        if (m < M) {
-#pragma unroll
-          for (int j = 0; j < 32; j++) {
-            const int n = n0 + c0 + j;
-            if (n >= N) continue;
-            if (cmode == C_UPPER && m > n) continue;
-            if (cmode == C_LOWER && m < n) continue;
-            float2* c = Cz + (size_t)m + (size_t)n * ldc;
-            const float xr = __uint_as_float(re[j]), xi = __uint_as_float(im[j]);
-            float2 v = make_float2(alpha * xr - alpha_im * xi, alpha * xi + alpha_im * xr);
-            if (!beta0) { const float2 o = *c; v.x += beta * o.x - beta_im * o.y; v.y += beta * o.y + beta_im * o.x; }
-            if (herk && m == n) v.y = 0.f;
-            *c = v;
-          }
-        }
-      }
-    }
+    tc_epilogue<CPLX>(tmem, q, lane, m0, n0, M, N, C, ldc, alpha, beta, alpha_im, beta_im, cmode, herk);
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   if (warp == 1) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(TMEM_COLS) : "memory");
+  }
+}
+
+// ---------------------------------------------------------------- CTA-pair variant (cta_group::2)
+// The single-CTA kernel is bound by the L2 -> shared-memory feed (96 KB per 128x256 tile step).  Here two CTAs
+// of a cluster (an SM pair) compute one 256x256 tile with tcgen05.mma.cta_group::2: each CTA stages its own 128
+// rows of A and only HALF of the B rows (the tensor core reads the other half from the peer's shared memory),
+// 64 KB per 128x256 of output, and holds its 128 rows of the accumulator in its own TMEM.  The even CTA of
+// the pair issues all MMAs; both CTAs' TMA loads complete on ITS full barrier (cp.async.bulk.tensor
+// .cta_group::2 with the peer bit of the barrier address cleared), and tcgen05.commit multicasts the
+// "stage free" / "accumulator ready" arrivals to both CTAs.
+constexpr int STAGE2_BYTES = 4 * A_TILE_BYTES;                 // A_hi, A_lo (128 rows), B_hi, B_lo (128 of the 256 rows)
+constexpr int STAGES2 = (192 * 1024) / STAGE2_BYTES;           // 3
+constexpr int SMEM2_BYTES = STAGES2 * STAGE2_BYTES + 1024 + 128;
+constexpr uint32_t IDESC2 = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(256 >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+
+__device__ __forceinline__ void tma_load_3d_2sm(uint32_t dst, const CUtensorMap* tm, int c0, int c1, int c2, uint32_t mbar) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tm)), "r"(c0), "r"(c1), "r"(c2), "r"(mbar) : "memory");
+}
+__device__ __forceinline__ void umma_tf32_2sm(uint32_t tmem_c, uint64_t da, uint64_t db, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_c), "l"(da), "l"(db), "r"(IDESC2), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit_2sm(uint32_t mbar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(mbar), "h"((uint16_t)3) : "memory");
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
+template <bool CPLX>
+__global__ void __launch_bounds__(THREADS, 1)
+sgemm_tc2_kernel(const __grid_constant__ CUtensorMap mAh, const __grid_constant__ CUtensorMap mAl,
+                 const __grid_constant__ CUtensorMap mBh, const __grid_constant__ CUtensorMap mBl, float* __restrict__ C, size_t ldc, int M,
+                 int N, int KB, float alpha, float beta, int cmode, int tiles_m, int tiles_n, const int* __restrict__ abort_flag,
+                 float alpha_im, float beta_im, int herk) {
+  if (abort_flag && *abort_flag) return;                 // (uniform over the grid: both CTAs of a pair leave)
+  constexpr int TN = CPLX ? BN / 2 : BN;
+  uint32_t rank;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(rank));
+  const int pair = (int)blockIdx.x >> 1;                  // tiles_m counts 256-row pair tiles here
+  constexpr int GM = 8;
+  const int in_group = GM * tiles_n;
+  const int first_m = (pair / in_group) * GM;
+  const int gsz = min(tiles_m - first_m, GM);
+  const int tn = (pair % in_group) / gsz;
+  const int pm0 = (first_m + (pair % in_group) % gsz) * 256, n0 = tn * TN;
+  if (cmode == C_UPPER && pm0 > n0 + TN - 1) return;      // the whole pair tile lies outside the triangle
+  if (cmode == C_LOWER && n0 > pm0 + 255) return;
+  const int m0 = pm0 + 128 * (int)rank;                   // this CTA's rows
+
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t bars = base + STAGES2 * STAGE2_BYTES;    // full[S], empty[S], accum
+  __shared__ uint32_t s_tmem;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES2; s++) { mbar_init(bars + 8 * s, 1); mbar_init(bars + 8 * (STAGES2 + s), 1); }
+    mbar_init(bars + 8 * (2 * STAGES2), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem)), "n"(TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  cluster_sync_all();                                      // both CTAs' barriers exist before any remote arrival
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem = s_tmem;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      for (int kb = 0; kb < KB; kb++) {
+        const int s = kb % STAGES2;
+        if (kb >= STAGES2) mbar_wait(bars + 8 * (STAGES2 + s), ((kb / STAGES2) - 1) & 1);
+        const uint32_t full = bars + 8 * s, dst = base + s * STAGE2_BYTES;
+        if (rank == 0) mbar_expect_tx(full, 2 * STAGE2_BYTES);       // the pair's bytes land on the even CTA's barrier
+        uint32_t full0;                                               // ... whose shared::cluster address is
+        asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(full0) : "r"(full), "r"(0));
+        tma_load_3d_2sm(dst, &mAh, 0, m0, kb, full0);
+        tma_load_3d_2sm(dst + A_TILE_BYTES, &mAl, 0, m0, kb, full0);
+        tma_load_3d_2sm(dst + 2 * A_TILE_BYTES, &mBh, 0, tn * BN + 128 * (int)rank, kb, full0);   // my half of the B rows
+        tma_load_3d_2sm(dst + 3 * A_TILE_BYTES, &mBl, 0, tn * BN + 128 * (int)rank, kb, full0);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0 && rank == 0) {
+      for (int kb = 0; kb < KB; kb++) {
+        const int s = kb % STAGES2;
+        mbar_wait(bars + 8 * s, (kb / STAGES2) & 1);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t sa = base + s * STAGE2_BYTES;
+#pragma unroll
+        for (int k4 = 0; k4 < BK / 8; k4++) {
+          const uint64_t ah = umma_desc(sa + k4 * 32), al = umma_desc(sa + A_TILE_BYTES + k4 * 32);
+          const uint64_t bh = umma_desc(sa + 2 * A_TILE_BYTES + k4 * 32), bl = umma_desc(sa + 3 * A_TILE_BYTES + k4 * 32);
+          umma_tf32_2sm(tmem, al, bh, (kb > 0 || k4 > 0) ? 1u : 0u);
+          umma_tf32_2sm(tmem, ah, bl, 1u);
+          umma_tf32_2sm(tmem, ah, bh, 1u);
+        }
+        umma_commit_2sm(bars + 8 * (STAGES2 + s));
+      }
+      umma_commit_2sm(bars + 8 * (2 * STAGES2));
+    }
+  } else {
+    mbar_wait(bars + 8 * (2 * STAGES2), 0);
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    tc_epilogue<CPLX>(tmem, warp & 3, lane, m0, n0, M, N, C, ldc, alpha, beta, alpha_im, beta_im, cmode, herk);
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  cluster_sync_all();                                      // nobody frees TMEM / leaves while the peer still uses the pair
+  if (warp == 1) {
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(TMEM_COLS) : "memory");
   }
 }
 
@@ -348,6 +478,38 @@ bool make_map(CUtensorMap* tm, const float* ptr, size_t Rp, size_t Kp, int box_r
 
 }  // namespace
 
+// ATLB200_SGEMM_TC=1: one CTA per 128x256 tile; default (2): CTA pairs (cta_group::2) on 256x256 tiles
+static int tc_variant() {
+  static const int v = [] { const char* e = getenv("ATLB200_SGEMM_TC"); const int x = e ? atoi(e) : 2; return x == 1 ? 1 : 2; }();
+  return v;
+}
+template <bool CPLX>
+static void launch_tc(const CUtensorMap& mAh, const CUtensorMap& mAl, const CUtensorMap& mBh, const CUtensorMap& mBl, float* C, size_t ldc, int M,
+                      int N, int KB, float alpha, float beta, int cmode, int tiles_m128, int tiles_n, const int* abort_flag, float alpha_im,
+                      float beta_im, int herk) {
+  if (tc_variant() == 2) {
+    static bool attr = false;
+    if (!attr) { AB_CUDA_CHECK(cudaFuncSetAttribute(sgemm_tc2_kernel<CPLX>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM2_BYTES)); attr = true; }
+    const int tiles_m256 = (tiles_m128 + 1) / 2;
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(2u * (unsigned)tiles_m256 * (unsigned)tiles_n); cfg.blockDim = dim3(THREADS);
+    cfg.dynamicSmemBytes = SMEM2_BYTES; cfg.stream = current_stream();
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    AB_CUDA_CHECK(cudaLaunchKernelEx(&cfg, sgemm_tc2_kernel<CPLX>, mAh, mAl, mBh, mBl, C, ldc, M, N, KB, alpha, beta, cmode, tiles_m256, tiles_n,
+                                     abort_flag, alpha_im, beta_im, herk));
+  } else {
+    static bool attr = false;
+    if (!attr) { AB_CUDA_CHECK(cudaFuncSetAttribute(sgemm_tc_kernel<CPLX>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES)); attr = true; }
+    sgemm_tc_kernel<CPLX><<<(unsigned)tiles_m128 * (unsigned)tiles_n, THREADS, SMEM_BYTES, current_stream()>>>(
+        mAh, mAl, mBh, mBl, C, ldc, M, N, KB, alpha, beta, cmode, tiles_m128, tiles_n, abort_flag, alpha_im, beta_im, herk);
+  }
+  count_launch();
+  AB_CUDA_CHECK(cudaGetLastError());
+}
+
 static bool ws_budget_ok(size_t bytes) {
   static const size_t budget = [] { const char* v = getenv("ATLB200_SGEMM_TC_WS_GB"); return (size_t)((v ? atof(v) : 20.0) * 1073741824.0); }();
   return bytes <= budget;
@@ -358,7 +520,7 @@ static bool ws_budget_ok(size_t bytes) {
 bool sgemm_tc(int ta, int tb, int M, int N, int K, float alpha, const float* A, size_t lda, const float* B, size_t ldb, float beta,
               float* C, size_t ldc, int cmode, const int* abort_flag) {
   if (M <= 0 || N <= 0 || K <= 0) return false;
-  const size_t Mp = ((size_t)M + BM - 1) / BM * BM, Np = ((size_t)N + BN - 1) / BN * BN, Kp = ((size_t)K + BK - 1) / BK * BK;
+  const size_t Mp = ((size_t)M + 255) / 256 * 256, Np = ((size_t)N + BN - 1) / BN * BN, Kp = ((size_t)K + BK - 1) / BK * BK;
   const size_t bytes = 2 * sizeof(float) * (Mp + Np) * Kp;
   if (!ws_budget_ok(bytes)) {
     // packed panels over the budget: halve the larger output dimension (the copy is O(N^2), repeating it is cheap)
@@ -392,16 +554,12 @@ bool sgemm_tc(int ta, int tb, int M, int N, int K, float alpha, const float* A, 
   count_launch(2);
   AB_CUDA_CHECK(cudaGetLastError());
   CUtensorMap mAh, mAl, mBh, mBl;
-  if (!make_map(&mAh, Ah, Mp, Kp, BM) || !make_map(&mAl, Al, Mp, Kp, BM) || !make_map(&mBh, Bh, Np, Kp, BN) || !make_map(&mBl, Bl, Np, Kp, BN)) {
+  const int brows = tc_variant() == 2 ? 128 : BN;      // a CTA of a pair stages half of the B rows
+  if (!make_map(&mAh, Ah, Mp, Kp, BM) || !make_map(&mAl, Al, Mp, Kp, BM) || !make_map(&mBh, Bh, Np, Kp, brows) || !make_map(&mBl, Bl, Np, Kp, brows)) {
     AB_CUDA_CHECK(cudaFreeAsync(ws, current_stream()));
     return false;
   }
-  static bool attr = false;
-  if (!attr) { AB_CUDA_CHECK(cudaFuncSetAttribute(sgemm_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES)); attr = true; }
-  sgemm_tc_kernel<false><<<(unsigned)tiles, THREADS, SMEM_BYTES, current_stream()>>>(mAh, mAl, mBh, mBl, C, ldc, M, N, (int)(Kp / BK), alpha, beta,
-                                                                                      cmode, (int)(Mp / BM), (int)(Np / BN), abort_flag, 0.f, 0.f, 0);
-  count_launch();
-  AB_CUDA_CHECK(cudaGetLastError());
+  launch_tc<false>(mAh, mAl, mBh, mBl, C, ldc, M, N, (int)(Kp / BK), alpha, beta, cmode, (int)(Mp / BM), (int)(Np / BN), abort_flag, 0.f, 0.f, 0);
   AB_CUDA_CHECK(cudaFreeAsync(ws, current_stream()));
   return true;
 }
@@ -411,7 +569,7 @@ bool cgemm_tc(int ta, int ca, int tb, int cb, int M, int N, int K, float2 alpha,
               float2 beta, float2* C, size_t ldc, int cmode, int herk, const int* abort_flag) {
   if (M <= 0 || N <= 0 || K <= 0) return false;
   constexpr int TNc = BN / 2;                                                   // complex columns per tile
-  const size_t Mp = ((size_t)M + BM - 1) / BM * BM, Np = ((size_t)N + TNc - 1) / TNc * TNc, Kp = ((size_t)K + BK - 1) / BK * BK;
+  const size_t Mp = ((size_t)M + 255) / 256 * 256, Np = ((size_t)N + TNc - 1) / TNc * TNc, Kp = ((size_t)K + BK - 1) / BK * BK;
   const size_t K2 = 2 * Kp;                                                     // doubled inner dimension
   const size_t bytes = 2 * sizeof(float) * (Mp + 2 * Np) * K2;
   if (!ws_budget_ok(bytes)) {
@@ -441,17 +599,13 @@ bool cgemm_tc(int ta, int ca, int tb, int cb, int M, int N, int K, float2 alpha,
   count_launch(2);
   AB_CUDA_CHECK(cudaGetLastError());
   CUtensorMap mAh, mAl, mBh, mBl;
-  if (!make_map(&mAh, Ah, Mp, K2, BM) || !make_map(&mAl, Al, Mp, K2, BM) || !make_map(&mBh, Bh, 2 * Np, K2, BN) || !make_map(&mBl, Bl, 2 * Np, K2, BN)) {
+  const int brows = tc_variant() == 2 ? 128 : BN;
+  if (!make_map(&mAh, Ah, Mp, K2, BM) || !make_map(&mAl, Al, Mp, K2, BM) || !make_map(&mBh, Bh, 2 * Np, K2, brows) || !make_map(&mBl, Bl, 2 * Np, K2, brows)) {
     AB_CUDA_CHECK(cudaFreeAsync(ws, current_stream()));
     return false;
   }
-  static bool attr = false;
-  if (!attr) { AB_CUDA_CHECK(cudaFuncSetAttribute(sgemm_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES)); attr = true; }
-  sgemm_tc_kernel<true><<<(unsigned)tiles, THREADS, SMEM_BYTES, current_stream()>>>(mAh, mAl, mBh, mBl, reinterpret_cast<float*>(C), ldc, M, N,
-                                                                                     (int)(K2 / BK), alpha.x, beta.x, cmode, (int)(Mp / BM),
-                                                                                     (int)(Np / TNc), abort_flag, alpha.y, beta.y, herk);
-  count_launch();
-  AB_CUDA_CHECK(cudaGetLastError());
+  launch_tc<true>(mAh, mAl, mBh, mBl, reinterpret_cast<float*>(C), ldc, M, N, (int)(K2 / BK), alpha.x, beta.x, cmode, (int)(Mp / BM), (int)(Np / TNc),
+                  abort_flag, alpha.y, beta.y, herk);
   AB_CUDA_CHECK(cudaFreeAsync(ws, current_stream()));
   return true;
 }
