@@ -157,8 +157,8 @@ struct DevInts {
 namespace {
 struct CopyStreams {
   cudaStream_t h2d = nullptr, d2h = nullptr;
-  static constexpr int NEV = 64;
-  cudaEvent_t in[NEV], done[NEV], a_in = nullptr, start = nullptr;
+  static constexpr int NEV = 64, NKC = 16;
+  cudaEvent_t in[NEV], done[NEV], kin[NKC], a_in = nullptr, start = nullptr;
   int dev = -1;
   void ensure() {
     int d; AB_CUDA_CHECK(cudaGetDevice(&d));
@@ -170,6 +170,7 @@ struct CopyStreams {
       AB_CUDA_CHECK(cudaEventCreateWithFlags(&in[i], cudaEventDisableTiming));
       AB_CUDA_CHECK(cudaEventCreateWithFlags(&done[i], cudaEventDisableTiming));
     }
+    for (int i = 0; i < NKC; i++) AB_CUDA_CHECK(cudaEventCreateWithFlags(&kin[i], cudaEventDisableTiming));
     AB_CUDA_CHECK(cudaEventCreateWithFlags(&a_in, cudaEventDisableTiming));
     AB_CUDA_CHECK(cudaEventCreateWithFlags(&start, cudaEventDisableTiming));
   }
@@ -200,25 +201,57 @@ static bool atl_gemm_pipelined(int TA, int TB, size_t M, size_t N, size_t K, T a
   AB_CUDA_CHECK(cudaEventRecord(cs.start, U));
   AB_CUDA_CHECK(cudaStreamWaitEvent(cs.h2d, cs.start, 0));
   AB_CUDA_CHECK(cudaStreamWaitEvent(cs.d2h, cs.start, 0));
-  if (a.staged)
-    AB_CUDA_CHECK(cudaMemcpy2DAsync(a.d, esz * a.ld, a.h, esz * a.ldh, esz * (size_t)a.rows, (size_t)a.cols, cudaMemcpyHostToDevice, cs.h2d));
-  AB_CUDA_CHECK(cudaEventRecord(cs.a_in, cs.h2d));
-  AB_CUDA_CHECK(cudaStreamWaitEvent(U, cs.a_in, 0));
   int np = (int)std::min<size_t>(CopyStreams::NEV, std::max<size_t>(2, N / 2048));
   const size_t pw = ((N + np - 1) / np + 127) / 128 * 128;   // panel width, multiple of the GEMM tile
   np = (int)((N + pw - 1) / pw);
-  for (int j = 0; j < np; j++) {
-    const size_t c0 = (size_t)j * pw, nc = std::min(pw, N - c0);
-    // H2D of this panel's B and C columns
-    if (!tB) AB_CUDA_CHECK(cudaMemcpy2DAsync(dB + c0 * ldbd, esz * ldbd, B + c0 * ldb, esz * ldb, esz * K, nc, cudaMemcpyHostToDevice, cs.h2d));
-    else     AB_CUDA_CHECK(cudaMemcpy2DAsync(dB + c0, esz * ldbd, B + c0, esz * ldb, esz * nc, K, cudaMemcpyHostToDevice, cs.h2d));
+  auto h2d_B = [&](size_t c0, size_t nc, size_t k0, size_t kc) {   // rows/cols [k0,k0+kc) x [c0,c0+nc) of op(B)
+    if (!tB) AB_CUDA_CHECK(cudaMemcpy2DAsync(dB + k0 + c0 * ldbd, esz * ldbd, B + k0 + c0 * ldb, esz * ldb, esz * kc, nc, cudaMemcpyHostToDevice, cs.h2d));
+    else     AB_CUDA_CHECK(cudaMemcpy2DAsync(dB + c0 + k0 * ldbd, esz * ldbd, B + c0 + k0 * ldb, esz * ldb, esz * nc, kc, cudaMemcpyHostToDevice, cs.h2d));
+  };
+  auto h2d_C = [&](size_t c0, size_t nc) {
     if (!beta0) AB_CUDA_CHECK(cudaMemcpy2DAsync(dC + c0 * ldcd, esz * ldcd, C + c0 * ldc, esz * ldc, esz * M, nc, cudaMemcpyHostToDevice, cs.h2d));
-    AB_CUDA_CHECK(cudaEventRecord(cs.in[j], cs.h2d));
-    AB_CUDA_CHECK(cudaStreamWaitEvent(U, cs.in[j], 0));
-    gemm<T>(TA, TB, (int)M, (int)nc, (int)K, alpha, a.d, a.ld, tB ? dB + c0 : dB + c0 * ldbd, ldbd, beta, dC + c0 * ldcd, ldcd);
+  };
+  auto d2h_C = [&](int j, size_t c0, size_t nc) {
     AB_CUDA_CHECK(cudaEventRecord(cs.done[j], U));
     AB_CUDA_CHECK(cudaStreamWaitEvent(cs.d2h, cs.done[j], 0));
     AB_CUDA_CHECK(cudaMemcpy2DAsync(C + c0 * ldc, esz * ldc, dC + c0 * ldcd, esz * ldcd, esz * M, nc, cudaMemcpyDeviceToHost, cs.d2h));
+  };
+  int j0 = 0;
+  if (a.staged && K >= 4096) {
+    // A comes from the host too: the first column panel is computed in K chunks while A is still
+    // arriving, C(:,panel 0) <- beta*C + alpha * sum_k A(:,k-chunk) * B(k-chunk, panel 0), so the upload
+    // of A hides behind tensor work instead of preceding all of it.
+    const int nk = (int)std::min<size_t>(CopyStreams::NKC, std::max<size_t>(2, K / 2048));
+    const size_t kw = ((K + nk - 1) / nk + 15) / 16 * 16;
+    const size_t nc = std::min(pw, N);
+    h2d_C(0, nc);
+    int q = 0;
+    for (size_t k0 = 0; k0 < K; k0 += kw, q++) {
+      const size_t kc = std::min(kw, K - k0);
+      if (!tA) AB_CUDA_CHECK(cudaMemcpy2DAsync(a.d + k0 * a.ld, esz * a.ld, a.h + k0 * a.ldh, esz * a.ldh, esz * M, kc, cudaMemcpyHostToDevice, cs.h2d));
+      else     AB_CUDA_CHECK(cudaMemcpy2DAsync(a.d + k0, esz * a.ld, a.h + k0, esz * a.ldh, esz * kc, M, cudaMemcpyHostToDevice, cs.h2d));
+      h2d_B(0, nc, k0, kc);
+      AB_CUDA_CHECK(cudaEventRecord(cs.kin[q], cs.h2d));
+      AB_CUDA_CHECK(cudaStreamWaitEvent(U, cs.kin[q], 0));
+      gemm<T>(TA, TB, (int)M, (int)nc, (int)kc, alpha, tA ? a.d + k0 : a.d + k0 * a.ld, a.ld, tB ? dB + k0 * ldbd : dB + k0, ldbd,
+              k0 == 0 ? beta : ST<T>::one(), dC, ldcd);
+    }
+    d2h_C(0, 0, nc);
+    j0 = 1;
+  } else {
+    if (a.staged)
+      AB_CUDA_CHECK(cudaMemcpy2DAsync(a.d, esz * a.ld, a.h, esz * a.ldh, esz * (size_t)a.rows, (size_t)a.cols, cudaMemcpyHostToDevice, cs.h2d));
+    AB_CUDA_CHECK(cudaEventRecord(cs.a_in, cs.h2d));
+    AB_CUDA_CHECK(cudaStreamWaitEvent(U, cs.a_in, 0));
+  }
+  for (int j = j0; j < np; j++) {
+    const size_t c0 = (size_t)j * pw, nc = std::min(pw, N - c0);
+    h2d_B(c0, nc, 0, K);
+    h2d_C(c0, nc);
+    AB_CUDA_CHECK(cudaEventRecord(cs.in[j], cs.h2d));
+    AB_CUDA_CHECK(cudaStreamWaitEvent(U, cs.in[j], 0));
+    gemm<T>(TA, TB, (int)M, (int)nc, (int)K, alpha, a.d, a.ld, tB ? dB + c0 : dB + c0 * ldbd, ldbd, beta, dC + c0 * ldcd, ldcd);
+    d2h_C(j, c0, nc);
   }
   AB_CUDA_CHECK(cudaStreamSynchronize(cs.d2h));
   AB_CUDA_CHECK(cudaStreamSynchronize(U));

@@ -322,3 +322,23 @@ def test_full_size_dgemm_and_dgetrf_properties(oracle):
     nrm = torch.max(torch.sum(torch.abs(R), dim=0)).item() / (torch.max(torch.sum(torch.abs(A0.T), dim=0)).item() * 2.0 ** -52 * n)
     assert nrm < LATHRESH, nrm
     assert torch.max(torch.abs(L)).item() <= 1.0 + 1e-12      # partial pivoting: |l_ij| <= 1
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("ta,tb", [(NoTrans, NoTrans), (Trans, Trans)])
+def test_host_pointer_pipeline_matches_device_path(ta, tb):
+    """cblas_dgemm with HOST arrays large enough for the column-panel / K-chunk pipeline (capi.cu
+    atl_gemm_pipelined) against the same call on device arrays: same kernels, other staging order."""
+    import torch
+    n = 4096
+    rng = np.random.default_rng(7)
+    A = np.asfortranarray(rng.random((n + 3, n)) - 0.5); B = np.asfortranarray(rng.random((n + 1, n)) - 0.5)
+    C0 = np.asfortranarray(rng.random((n + 2, n)) - 0.5)
+    got = C0.copy(order="F")
+    ab.cblas_dgemm(ColMajor, ta, tb, n, n, n, -1.1, A, n + 3, B, n + 1, 0.7, got, n + 2)
+    dA, dB, dC = (torch.from_numpy(np.ascontiguousarray(X.T)).cuda() for X in (A, B, C0))
+    ab.cblas_dgemm(ColMajor, ta, tb, n, n, n, -1.1, dA, n + 3, dB, n + 1, 0.7, dC, n + 2)
+    want = dC.cpu().numpy().T
+    assert np.array_equal(got[n:], C0[n:]), "lda gap overwritten"
+    err = np.max(np.abs(got[:n] - want[:n]))
+    assert err < 64 * np.finfo(np.float64).eps * n * 0.25, err      # summation order differs (K chunks), nothing else
