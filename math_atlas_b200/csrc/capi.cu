@@ -858,6 +858,78 @@ CPLX_L3X(c, cfloat, float)
 CPLX_L3X(z, cdouble, double)
 }
 
+// ---- F77 front ends of SYMM / HEMM / SYR2K / HER2K (netlib argument numbering)
+template <typename T>
+static void f_symm(const char* name, int herm, const char* sd, const char* ul, const int* m, const int* n, const T* alpha, const T* A,
+                   const int* lda, const T* B, const int* ldb, const T* beta, T* C, const int* ldc) {
+  const int SD = f_side(sd), UL = f_uplo(ul);
+  const int nrowa = (SD == Left) ? *m : *n;
+  int info = 0;
+  if (SD < 0) info = 1;
+  else if (UL < 0) info = 2;
+  else if (*m < 0) info = 3;
+  else if (*n < 0) info = 4;
+  else if (*lda < imax(1, nrowa)) info = 7;
+  else if (*ldb < imax(1, *m)) info = 9;
+  else if (*ldc < imax(1, *m)) info = 12;
+  if (f_err(name, info)) return;
+  atl_symm<T>(herm, SD, UL, *m, *n, *alpha, A, *lda, B, *ldb, *beta, C, *ldc);
+}
+template <typename T>
+static void f_syr2k(const char* name, const char* ul, const char* tr, const int* n, const int* k, const T* alpha, const T* A, const int* lda,
+                    const T* B, const int* ldb, const T* beta, T* C, const int* ldc) {
+  const int UL = f_uplo(ul), TR = f_trans(tr);
+  const int nrowa = (TR == NoTrans) ? *n : *k;
+  int info = 0;
+  if (UL < 0) info = 1;
+  else if (TR < 0 || (ST<T>::cplx && TR == ConjTrans)) info = 2;
+  else if (*n < 0) info = 3;
+  else if (*k < 0) info = 4;
+  else if (*lda < imax(1, nrowa)) info = 7;
+  else if (*ldb < imax(1, nrowa)) info = 9;
+  else if (*ldc < imax(1, *n)) info = 12;
+  if (f_err(name, info)) return;
+  atl_syr2k<T>(UL, TR == NoTrans ? NoTrans : TransT, *n, *k, *alpha, A, *lda, B, *ldb, *beta, C, *ldc);
+}
+template <typename T>
+static void f_her2k(const char* name, const char* ul, const char* tr, const int* n, const int* k, const T* alpha, const T* A, const int* lda,
+                    const T* B, const int* ldb, const typename ST<T>::real* beta, T* C, const int* ldc) {
+  const int UL = f_uplo(ul), TR = f_trans(tr);
+  const int nrowa = (TR == NoTrans) ? *n : *k;
+  int info = 0;
+  if (UL < 0) info = 1;
+  else if (TR != NoTrans && TR != ConjTrans) info = 2;
+  else if (*n < 0) info = 3;
+  else if (*k < 0) info = 4;
+  else if (*lda < imax(1, nrowa)) info = 7;
+  else if (*ldb < imax(1, nrowa)) info = 9;
+  else if (*ldc < imax(1, *n)) info = 12;
+  if (f_err(name, info)) return;
+  atl_her2k<T>(UL, TR, *n, *k, *alpha, A, *lda, B, *ldb, *beta, C, *ldc);
+}
+extern "C" {
+#define F77_L3X(P, T, AT, UP)                                                                                                      \
+  void P##symm_(const char* sd, const char* ul, const int* m, const int* n, const AT* alpha, const AT* A, const int* lda, const AT* B, \
+                const int* ldb, const AT* beta, AT* C, const int* ldc, size_t, size_t) {                                          \
+    f_symm<T>(UP "SYMM ", 0, sd, ul, m, n, CP(T, alpha), CP(T, A), lda, CP(T, B), ldb, CP(T, beta), MP(T, C), ldc); }              \
+  void P##syr2k_(const char* ul, const char* tr, const int* n, const int* k, const AT* alpha, const AT* A, const int* lda, const AT* B, \
+                 const int* ldb, const AT* beta, AT* C, const int* ldc, size_t, size_t) {                                         \
+    f_syr2k<T>(UP "SYR2K", ul, tr, n, k, CP(T, alpha), CP(T, A), lda, CP(T, B), ldb, CP(T, beta), MP(T, C), ldc); }
+F77_L3X(s, float, float, "S")
+F77_L3X(d, double, double, "D")
+F77_L3X(c, cfloat, void, "C")
+F77_L3X(z, cdouble, void, "Z")
+#define F77_L3H(P, T, R, UP)                                                                                                       \
+  void P##hemm_(const char* sd, const char* ul, const int* m, const int* n, const void* alpha, const void* A, const int* lda,      \
+                const void* B, const int* ldb, const void* beta, void* C, const int* ldc, size_t, size_t) {                        \
+    f_symm<T>(UP "HEMM ", 1, sd, ul, m, n, CP(T, alpha), CP(T, A), lda, CP(T, B), ldb, CP(T, beta), MP(T, C), ldc); }              \
+  void P##her2k_(const char* ul, const char* tr, const int* n, const int* k, const void* alpha, const void* A, const int* lda,     \
+                 const void* B, const int* ldb, const R* beta, void* C, const int* ldc, size_t, size_t) {                          \
+    f_her2k<T>(UP "HER2K", ul, tr, n, k, CP(T, alpha), CP(T, A), lda, CP(T, B), ldb, beta, MP(T, C), ldc); }
+F77_L3H(c, cfloat, float, "C")
+F77_L3H(z, cdouble, double, "Z")
+}
+
 // ------------------------------------------------------------------------------------- solve / inverse layer
 // getrs/potrs/gesv/posv/trtri/lauum/getri/potri (reference
 // Clint/atlas-lp.base:16-331, 969-1052, 1631-2381; wrappers Clint/atlas-clp.base:62-454).
