@@ -16,7 +16,13 @@ OBJ = os.path.join(CSRC, "obj")
 LIB = os.path.join(HERE, "libatlas_b200.so")
 SOURCES = ["runtime.cu", "dgemm_tma.cu", "zgemm_tma.cu", "sgemm_ffma.cu", "sgemm_tc.cu", "cgemm_ffma.cu", "level3.cu", "lapack.cu", "lapack_inv.cu", "capi.cu", "probe.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC",
-              "--expt-relaxed-constexpr", "-diag-suppress", "177,550"]
+              "--expt-relaxed-constexpr", "-diag-suppress", "177,550",
+              # Global loads bypass L1 (ld.global.cg).  The factorisations run two streams; an SM that stays occupied by
+              # one stream's long kernel is not L1-invalidated when the other stream's next kernel starts on it, so a
+              # load through L1 can return a line cached before another SM rewrote it (measured: clapack_dgetrf
+              # N=16384 changed pivots in 1 of 60 runs, in 59 of 60 with the update GEMM forced to overlap the panel).
+              # L2 is the coherence point; nothing here reuses data through L1 (tiles live in shared memory).
+              "-Xptxas", "-dlcm=cg"]
 
 
 def _needs(obj, deps):

@@ -23,7 +23,7 @@ struct CParams {
 };
 
 // 64 x 8 complex = 2 per thread.  MN-contiguous: element (r,k) at P[r + k*ld], 2 consecutive r per thread.
-__device__ __forceinline__ void load_mn(float2 (&v)[2], const float2* __restrict__ P, size_t ld, int r0, int k0, int R, int K, int vec, int cj) {
+__device__ __forceinline__ void load_mn(float2 (&v)[2], const float2* P, size_t ld, int r0, int k0, int R, int K, int vec, int cj) {
   const int r = r0 + (threadIdx.x & 31) * 2, k = k0 + (threadIdx.x >> 5);
   if (k < K && r + 1 < R && vec) {
     const float4 t = *reinterpret_cast<const float4*>(P + (size_t)r + (size_t)k * ld);
@@ -35,7 +35,7 @@ __device__ __forceinline__ void load_mn(float2 (&v)[2], const float2* __restrict
   if (cj) { v[0].y = -v[0].y; v[1].y = -v[1].y; }
 }
 // K-contiguous: element (r,k) at P[k + r*ld], 2 consecutive k of one r per thread.
-__device__ __forceinline__ void load_k(float2 (&v)[2], const float2* __restrict__ P, size_t ld, int r0, int k0, int R, int K, int vec, int cj) {
+__device__ __forceinline__ void load_k(float2 (&v)[2], const float2* P, size_t ld, int r0, int k0, int R, int K, int vec, int cj) {
   const int r = r0 + (threadIdx.x >> 2), k = k0 + (threadIdx.x & 3) * 2;
   if (r < R && k + 1 < K && vec) {
     const float4 t = *reinterpret_cast<const float4*>(P + (size_t)k + (size_t)r * ld);

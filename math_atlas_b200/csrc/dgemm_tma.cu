@@ -22,6 +22,7 @@
 #include "dgemm_tma.h"
 #include <cuda.h>
 #include <mutex>
+#include <cstdlib>
 #include <algorithm>
 
 namespace ab {
@@ -113,8 +114,10 @@ template <bool A_KMAJOR, bool B_KMAJOR>
 __global__ void __launch_bounds__(THREADS, 1)
 dgemm_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                  double* __restrict__ C, size_t ldc, int M, int N, int K, double alpha, double beta,
-                 int cmode, int tiles_m, int tiles_n, const int* __restrict__ abort_flag,
-                 const SmMask reserved, int* __restrict__ tile_counter) {
+                 int cmode, int tiles_m, int tiles_n, const int* abort_flag,
+                 const SmMask reserved, int* tile_counter) {
+  const bool no_prefetch = (cmode & 0x100) != 0;    // debug bit (ATLB200_DEBUG_NO_CPREFETCH)
+  cmode &= 0xff;
   if (abort_flag && *abort_flag) return;  // POTRF stop-at-first-failure (uniform for the whole grid)
   {
     const unsigned sm = my_smid();
@@ -198,7 +201,7 @@ dgemm_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     int m0, n0;
     tile_coords(tile, tiles_m, tiles_n, m0, n0);
 
-    if (!beta0) {
+    if (!beta0 && !no_prefetch) {
       // bring this tile's C block (128 columns x 1 KiB) into L2 while the k loop runs: thread i of
       // the 256 consumers takes column i/2, half i%2, four 128-byte lines
       const int ctid = (int)threadIdx.x;               // consumer warps are 0..7
@@ -333,6 +336,8 @@ void launch(const CUtensorMap& ta, const CUtensorMap& tb, double* C, size_t ldc,
     AB_CUDA_CHECK(cudaFuncSetAttribute(dgemm_tma_kernel<AK, BK_>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
     attr_set = true;
   }
+  static const bool dbg_nopf = getenv("ATLB200_DEBUG_NO_CPREFETCH") != nullptr;
+  if (dbg_nopf) cmode |= 0x100;
   const int tiles_m = (M + BM - 1) / BM, tiles_n = (N + BN - 1) / BN;
   int grid = std::min(tiles_m * tiles_n, gemm_cta_cap());
   SmMask mask = {{0, 0, 0, 0}};

@@ -34,8 +34,8 @@ namespace ab {
 // holds pivot i+b (one coalesced load, prefetched one batch ahead); the alias test is a
 // __match_any / __any over the warp, and every thread gets pivot b by shuffle.
 template <typename T>
-__global__ void __launch_bounds__(64) laswp_kernel(int N, T* __restrict__ A, size_t lda, int K1, int K2,
-                                                    const int* __restrict__ piv, int inci) {
+__global__ void __launch_bounds__(64) laswp_kernel(int N, T* A, size_t lda, int K1, int K2,
+                                                    const int* piv, int inci) {
   const int col = blockIdx.x * blockDim.x + threadIdx.x;
   const bool active = col < N;
   const int lane = threadIdx.x & 31;
@@ -132,9 +132,9 @@ __device__ __forceinline__ void grid_barrier(unsigned* counter, unsigned target)
 //   jrow[j][W]   (T)      contents of row j before the swap
 template <typename T, int W, int RPT>
 __global__ void __launch_bounds__(PNL_THREADS)
-getf2_panel_kernel(int M, int w, T* __restrict__ A, size_t lda, int* __restrict__ ipiv, int* __restrict__ info,
-                   int piv_off, int info_off, unsigned* __restrict__ counter, typename ST<T>::real* __restrict__ cval, int* __restrict__ crow,
-                   T* __restrict__ crows, T* __restrict__ jrow) {
+getf2_panel_kernel(int M, int w, T* A, size_t lda, int* ipiv, int* info,
+                   int piv_off, int info_off, unsigned* counter, typename ST<T>::real* cval, int* crow,
+                   T* crows, T* jrow) {
   using S = ST<T>;
   using R = typename S::real;
   const int nb = gridDim.x, b = blockIdx.x, tid = threadIdx.x;
@@ -410,6 +410,7 @@ static void getrf_rec(T* A0, size_t lda, int r0, int M, int N, int* d_ipiv, int*
 // while the main stream applies update k to the rest of the trailing matrix.  Pivoting is
 // unchanged (the same column-by-column search on the same updated values).
 namespace {
+int env_int(const char* name, int dflt);
 struct SideStream {
   cudaStream_t st = nullptr;
   cudaEvent_t cols[2] = {nullptr, nullptr}, panel[2] = {nullptr, nullptr};
@@ -418,7 +419,7 @@ struct SideStream {
     int d; AB_CUDA_CHECK(cudaGetDevice(&d));
     if (st && d == dev) return;
     dev = d;
-    AB_CUDA_CHECK(cudaStreamCreateWithPriority(&st, cudaStreamNonBlocking, -1));   // panel work first
+    AB_CUDA_CHECK(cudaStreamCreateWithPriority(&st, cudaStreamNonBlocking, env_int("ATLB200_LU_SIDE_PRIO", -1)));   // panel work first
     for (int i = 0; i < 2; i++) {
       AB_CUDA_CHECK(cudaEventCreateWithFlags(&cols[i], cudaEventDisableTiming));
       AB_CUDA_CHECK(cudaEventCreateWithFlags(&panel[i], cudaEventDisableTiming));
@@ -486,8 +487,30 @@ static void getrf_lookahead(int M, int N, T* A, size_t lda, int* d_ipiv, int* d_
         set_current_stream(U);
         set_gemm_reserved(reserved);                                   // leave a GPC to the panel kernels
       }
+      // What runs beside the panel.  The row interchanges (of the rest columns and left of the panel) always
+      // do.  The rest update's TRSM and GEMM do only with ATLB200_LU_OVERLAP_GEMM=1: although it
+      // shares no data with the panel, a stress test (tools/lu_stress.py) found clapack_dgetrf N=16384
+      // changing pivots in ~2 % of the runs whenever the long persistent GEMM ran beside the panel's
+      // kernels (never with any other overlap, never on one stream; L1-bypassing loads cut the rate but did
+      // not remove it) - until that is understood the GEMM waits for the panel.
+      static const bool overlap_gemm = env_int("ATLB200_LU_OVERLAP_GEMM", 0) != 0;
+      const int c0 = c1 + w1, nc = nright - w1;
       if (more) mark(U);
-      lu_apply_panel<T>(A, lda, M, k0, w, c1 + w1, nright - w1, d_ipiv);
+      if (more && !overlap_gemm) {
+        using S = ST<T>;
+        set_gemm_reserved(nullptr);
+        if (nc > 0) laswp<T>(nc, A + (size_t)c0 * lda, lda, k0, k0 + w, d_ipiv, 1);
+        if (k0 > 0) laswp<T>(k0, A, lda, k0, k0 + w, d_ipiv, 1);         // interchanges left of the panel
+        AB_CUDA_CHECK(cudaStreamWaitEvent(U, ss.panel[k & 1], 0));
+        if (nc > 0)       // (the TRSM recursion contains GEMMs of its own: after the panel, too)
+          trsm<T>(Left, Lower, NoTrans, Unit, w, nc, S::one(), A + (size_t)k0 + (size_t)k0 * lda, lda, A + (size_t)k0 + (size_t)c0 * lda, lda);
+        if (nc > 0 && M - k0 - w > 0)
+          gemm<T>(NoTrans, NoTrans, M - k0 - w, nc, w, S::from_real(-1), A + (size_t)(k0 + w) + (size_t)k0 * lda, lda,
+                  A + (size_t)k0 + (size_t)c0 * lda, lda, S::one(), A + (size_t)(k0 + w) + (size_t)c0 * lda, lda);
+        mark(U);
+        continue;
+      }
+      lu_apply_panel<T>(A, lda, M, k0, w, c0, nc, d_ipiv);
       if (more) mark(U);
       set_gemm_reserved(nullptr);
     }
@@ -537,7 +560,7 @@ constexpr int PF_NB = 32;
 
 template <typename T>
 __global__ void __launch_bounds__(PF_NB * PF_NB / 4)
-potf2_kernel(int upper, int n, T* __restrict__ A, size_t lda, int* __restrict__ info, int info_off) {
+potf2_kernel(int upper, int n, T* A, size_t lda, int* info, int info_off) {
   using S = ST<T>;
   using R = typename S::real;
   if (*info != 0) return;

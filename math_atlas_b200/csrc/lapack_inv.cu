@@ -39,7 +39,7 @@ __global__ void conj_kernel(int M, int N, T* B, size_t ldb) {
 
 // info <- 1-based index of the first exactly-zero diagonal element, 0 if none (one CTA)
 template <typename T>
-__global__ void diag_zero_kernel(int N, const T* __restrict__ A, size_t lda, int* __restrict__ info) {
+__global__ void diag_zero_kernel(int N, const T* A, size_t lda, int* info) {
   __shared__ int s_min;
   if (threadIdx.x == 0) s_min = INT_MAX;
   __syncthreads();
@@ -53,7 +53,7 @@ __global__ void diag_zero_kernel(int N, const T* __restrict__ A, size_t lda, int
 
 // inverse of an n x n (n <= 32) triangle in place, thread j computes column j of the inverse
 template <typename T>
-__global__ void __launch_bounds__(INV_NB) trti2_kernel(int upper, int unit, int n, T* __restrict__ A, size_t lda) {
+__global__ void __launch_bounds__(INV_NB) trti2_kernel(int upper, int unit, int n, T* A, size_t lda) {
   using S = ST<T>;
   __shared__ T t[INV_NB][INV_NB + 1], x[INV_NB][INV_NB + 1], dinv[INV_NB];
   const int j = threadIdx.x;
@@ -90,7 +90,7 @@ __global__ void __launch_bounds__(INV_NB) trti2_kernel(int upper, int unit, int 
 
 // n <= 32: the triangle of U*U^H (upper) or L^H*L (lower) in place
 template <typename T>
-__global__ void __launch_bounds__(INV_NB * INV_NB) lauu2_kernel(int upper, int n, T* __restrict__ A, size_t lda) {
+__global__ void __launch_bounds__(INV_NB * INV_NB) lauu2_kernel(int upper, int n, T* A, size_t lda) {
   using S = ST<T>;
   __shared__ T t[INV_NB][INV_NB + 1];
   const int i = threadIdx.x % INV_NB, j = threadIdx.x / INV_NB;
@@ -107,7 +107,7 @@ __global__ void __launch_bounds__(INV_NB * INV_NB) lauu2_kernel(int upper, int n
 
 // C (ldc) <- strictly lower part of the M x N block L, which is zeroed (reference trcpzeroL, :115-133)
 template <typename T>
-__global__ void trcpzero_kernel(int M, int N, T* __restrict__ L, size_t ldl, T* __restrict__ C, size_t ldc) {
+__global__ void trcpzero_kernel(int M, int N, T* L, size_t ldl, T* C, size_t ldc) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x, j = blockIdx.y;
   if (i < M && j < N && i > j) {
     C[(size_t)i + (size_t)j * ldc] = L[(size_t)i + (size_t)j * ldl];
@@ -117,7 +117,7 @@ __global__ void trcpzero_kernel(int M, int N, T* __restrict__ L, size_t ldl, T* 
 
 // column interchanges of getri: for J = N-2 .. 0 swap columns J and ipiv[J]; one thread per row
 template <typename T>
-__global__ void colswap_kernel(int N, T* __restrict__ A, size_t lda, const int* __restrict__ ipiv) {
+__global__ void colswap_kernel(int N, T* A, size_t lda, const int* ipiv) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= N) return;
   T* a = A + i;

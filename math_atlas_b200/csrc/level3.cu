@@ -38,6 +38,8 @@ static void gemm_flags(int ta, int ca, int tb, int cb, int M, int N, int K, T al
     return;
   }
   if constexpr (std::is_same<T, double>::value) {
+    static const bool side_generic = getenv("ATLB200_DEBUG_SIDE_GENERIC") != nullptr;   // bisecting tool
+    if (side_generic && current_stream() != nullptr) { gemm_generic_launch(p); return; }
     if ((double)M * N * K >= 262144.0 && !herk &&
         dgemm_tma(ta, tb, M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, cmode, abort_flag))
       return;
@@ -209,7 +211,7 @@ __device__ __forceinline__ double2 shfl_t(double2 v, int src) { return make_doub
 template <typename T, int NB>
 __global__ void __launch_bounds__(TS_VEC * TS_Q)
 trsm_base_kernel(int left, int tt /*Tm(i,l) = tt ? A[l+i*lda] : A[i+l*lda]*/, int cj, int unit, int rev, int n, int nvec,
-                 T alpha, const T* __restrict__ A, size_t lda, T* __restrict__ B, size_t ldb, const int* abort_flag) {
+                 T alpha, const T* A, size_t lda, T* B, size_t ldb, const int* abort_flag) {
   using S = ST<T>;
   constexpr int RP = NB / TS_Q;            // rows per thread
   if (abort_flag && *abort_flag) return;
@@ -359,7 +361,7 @@ void trsm(int side, int uplo, int trans, int diag, int M, int N, T alpha, const 
 // and runs its GEMM loops; here the triangle is expanded once into a dense workspace matrix
 // (O(n^2) against the O(n^2 m) multiply) and the fast GEMM kernels do the rest.
 template <typename T>
-__global__ void symmetrize_kernel(int upper, int herm, int n, const T* __restrict__ A, size_t lda, T* __restrict__ W, size_t ldw) {
+__global__ void symmetrize_kernel(int upper, int herm, int n, const T* A, size_t lda, T* W, size_t ldw) {
   using S = ST<T>;
   const int i = blockIdx.x * blockDim.x + threadIdx.x, j = blockIdx.y * blockDim.y + threadIdx.y;
   if (i >= n || j >= n) return;

@@ -143,7 +143,7 @@ __device__ __forceinline__ void cluster_arrive_wait() {
 
 template <typename T, int W, int RPT>
 __global__ void __launch_bounds__(CL_TPB, 1)
-getf2_cluster_kernel(int M, int w, T* __restrict__ A, size_t lda, int* __restrict__ ipiv, int* __restrict__ info,
+getf2_cluster_kernel(int M, int w, T* A, size_t lda, int* ipiv, int* info,
                      int piv_off, int info_off) {
   using S = ST<T>;
   using R = typename S::real;
@@ -316,8 +316,8 @@ __device__ __forceinline__ void cl_mbar_wait(unsigned a, unsigned parity) {
 
 template <typename T, int W, int RPT>
 __global__ void __launch_bounds__(CL_TPB, 1)
-getf2_cluster_async_kernel(int M, int w, T* __restrict__ A, size_t lda, int* __restrict__ ipiv, int* __restrict__ info,
-                           int piv_off, int info_off, long long* __restrict__ prof = nullptr) {
+getf2_cluster_async_kernel(int M, int w, T* A, size_t lda, int* ipiv, int* info,
+                           int piv_off, int info_off, long long* prof = nullptr) {
   // prof (tools/leaf_profile.cu only): clock64 stamps of warps 0 and 3 of every CTA at 7 points per column
 #define AB_STAMP(k) do { if (prof && lane == 0 && (wid == 0 || wid == 3)) s_prof[wid ? 1 : 0][j][k] = clock64(); } while (0)
   __shared__ long long s_prof[2][W][8];

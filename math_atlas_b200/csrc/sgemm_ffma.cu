@@ -26,7 +26,7 @@ struct SParams {
 
 // ---- tile loaders: 128 x 8 floats = 4 per thread, fetched into registers ----
 // MN-contiguous operand (A NoTrans / B Trans): element (r, k) at P[r + k*ld]; thread takes 4 consecutive r
-__device__ __forceinline__ void load_mn(float (&v)[4], const float* __restrict__ P, size_t ld, int r0, int k0, int R, int K, int vec) {
+__device__ __forceinline__ void load_mn(float (&v)[4], const float* P, size_t ld, int r0, int k0, int R, int K, int vec) {
   const int r = r0 + (threadIdx.x & 31) * 4, k = k0 + (threadIdx.x >> 5);
   if (k < K && r + 3 < R && vec) {
     const float4 t = *reinterpret_cast<const float4*>(P + (size_t)r + (size_t)k * ld);
@@ -37,7 +37,7 @@ __device__ __forceinline__ void load_mn(float (&v)[4], const float* __restrict__
   }
 }
 // K-contiguous operand (A Trans / B NoTrans): element (r, k) at P[k + r*ld]; thread takes 4 consecutive k of one r
-__device__ __forceinline__ void load_k(float (&v)[4], const float* __restrict__ P, size_t ld, int r0, int k0, int R, int K, int vec) {
+__device__ __forceinline__ void load_k(float (&v)[4], const float* P, size_t ld, int r0, int k0, int R, int K, int vec) {
   const int r = r0 + (threadIdx.x >> 1), k = k0 + (threadIdx.x & 1) * 4;
   if (r < R && k + 3 < K && vec) {
     const float4 t = *reinterpret_cast<const float4*>(P + (size_t)k + (size_t)r * ld);

@@ -97,8 +97,8 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
 // Access-major panels: P_hi/P_lo[((k/32) * Rp + r) * 32 + k%32] for r < Rp, k < Kp (zero padded), so the 128 x 32
 // (256 x 32) block one TMA instruction fetches is one contiguous 16 (32) KB piece of memory - ATLAS's block-major
 // copy format.  op(X)(r,k) = X[r + k*ld] (kcontig=0) or X[k + r*ld] (kcontig=1)
-__global__ void __launch_bounds__(256) split_pack_kernel(int R, int K, int Rp, int Kp, const float* __restrict__ X, size_t ld, int kcontig,
-                                                         float* __restrict__ Ph, float* __restrict__ Pl) {
+__global__ void __launch_bounds__(256) split_pack_kernel(int R, int K, int Rp, int Kp, const float* X, size_t ld, int kcontig,
+                                                         float* Ph, float* Pl) {
   __shared__ float t[32][33];
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;     // 32 x 8
   const int r0 = blockIdx.y * 32, k0 = blockIdx.x * 32;
@@ -132,7 +132,7 @@ __global__ void __launch_bounds__(256) split_pack_kernel(int R, int K, int Rp, i
   }
 }
 
-__device__ __forceinline__ void split_store(float* __restrict__ Ph, float* __restrict__ Pl, size_t o, float a) {
+__device__ __forceinline__ void split_store(float* Ph, float* Pl, size_t o, float a) {
   uint32_t hb, lb;
   asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hb) : "f"(a));
   const float hi = __uint_as_float(hb);
@@ -145,8 +145,8 @@ __device__ __forceinline__ void split_store(float* __restrict__ Ph, float* __res
 //   isB = 0: packed row r:  [ re(r,k) | im(r,k) ]                                   (Rp rows)
 //   isB = 1: complex column n -> packed rows 256*(n/128) + n%128 ("re" row): [ re(k,n) | -im(k,n) ]
 //                                        and 256*(n/128) + 128 + n%128 ("im" row): [ im(k,n) |  re(k,n) ]
-__global__ void __launch_bounds__(256) split_pack_cplx_kernel(int R, int K, int Rp, int Kp, const float2* __restrict__ X, size_t ld,
-                                                              int kcontig, int cj, int isB, float* __restrict__ Ph, float* __restrict__ Pl) {
+__global__ void __launch_bounds__(256) split_pack_cplx_kernel(int R, int K, int Rp, int Kp, const float2* X, size_t ld,
+                                                              int kcontig, int cj, int isB, float* Ph, float* Pl) {
   __shared__ float2 t[32][33];
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
   const int r0 = blockIdx.y * 32, k0 = blockIdx.x * 32, KBh = Kp / 32;
@@ -188,7 +188,7 @@ __global__ void __launch_bounds__(256) split_pack_cplx_kernel(int R, int K, int 
 // ---------------------------------------------------------------- the tensor-core kernel
 // C = alpha*acc + beta*C for the 32 tile rows of TMEM lane quarter q (rows m0 + 32q + lane), all TN output columns
 template <bool CPLX>
-__device__ __forceinline__ void tc_epilogue(uint32_t tmem, int q, int lane, int m0, int n0, int M, int N, float* __restrict__ C, size_t ldc,
+__device__ __forceinline__ void tc_epilogue(uint32_t tmem, int q, int lane, int m0, int n0, int M, int N, float* C, size_t ldc,
                                             float alpha, float beta, float alpha_im, float beta_im, int cmode, int herk) {
   constexpr int TN = CPLX ? BN / 2 : BN;
   const int m = m0 + q * 32 + lane;
@@ -247,8 +247,8 @@ __device__ __forceinline__ void tc_epilogue(uint32_t tmem, int q, int lane, int 
 template <bool CPLX>
 __global__ void __launch_bounds__(THREADS, 1)
 sgemm_tc_kernel(const __grid_constant__ CUtensorMap mAh, const __grid_constant__ CUtensorMap mAl,
-                const __grid_constant__ CUtensorMap mBh, const __grid_constant__ CUtensorMap mBl, float* __restrict__ C, size_t ldc, int M,
-                int N, int KB, float alpha, float beta, int cmode, int tiles_m, int tiles_n, const int* __restrict__ abort_flag,
+                const __grid_constant__ CUtensorMap mBh, const __grid_constant__ CUtensorMap mBl, float* C, size_t ldc, int M,
+                int N, int KB, float alpha, float beta, int cmode, int tiles_m, int tiles_n, const int* abort_flag,
                 float alpha_im, float beta_im, int herk) {
   if (abort_flag && *abort_flag) return;
   constexpr int TN = CPLX ? BN / 2 : BN;               // output columns per tile (complex: 128)
@@ -363,8 +363,8 @@ __device__ __forceinline__ void cluster_sync_all() {
 template <bool CPLX>
 __global__ void __launch_bounds__(THREADS, 1)
 sgemm_tc2_kernel(const __grid_constant__ CUtensorMap mAh, const __grid_constant__ CUtensorMap mAl,
-                 const __grid_constant__ CUtensorMap mBh, const __grid_constant__ CUtensorMap mBl, float* __restrict__ C, size_t ldc, int M,
-                 int N, int KB, float alpha, float beta, int cmode, int tiles_m, int tiles_n, const int* __restrict__ abort_flag,
+                 const __grid_constant__ CUtensorMap mBh, const __grid_constant__ CUtensorMap mBl, float* C, size_t ldc, int M,
+                 int N, int KB, float alpha, float beta, int cmode, int tiles_m, int tiles_n, const int* abort_flag,
                  float alpha_im, float beta_im, int herk) {
   if (abort_flag && *abort_flag) return;                 // (uniform over the grid: both CTAs of a pair leave)
   constexpr int TN = CPLX ? BN / 2 : BN;

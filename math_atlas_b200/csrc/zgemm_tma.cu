@@ -74,8 +74,8 @@ __device__ __forceinline__ bool tile_skipped(int cmode, int m0, int n0) {
 template <bool A_KMAJOR, bool B_KMAJOR>
 __global__ void __launch_bounds__(THREADS, 1)
 zgemm_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                 double2* __restrict__ C, size_t ldc, int M, int N, int K, double2 alpha, double2 beta,
-                 int conjA, int conjB, int cmode, int herk, int tiles_m, int tiles_n, const int* __restrict__ abort_flag) {
+                 double2* C, size_t ldc, int M, int N, int K, double2 alpha, double2 beta,
+                 int conjA, int conjB, int cmode, int herk, int tiles_m, int tiles_n, const int* abort_flag) {
   if (abort_flag && *abort_flag) return;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;

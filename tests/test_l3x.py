@@ -97,24 +97,24 @@ def test_gpu_f77_symm_syr2k_her2k_match_cblas(oracle):
     vp = lambda a: C.c_void_p(a.ctypes.data)
     A = oracle.gegen("d", M, M, M, 1); B = oracle.gegen("d", M, N, M, 2); C0 = oracle.gegen("d", M, N, M, 3)
     want, got = C0.copy(order="F"), C0.copy(order="F")
-    ab.cblas_dsymm(ColMajor, Left, Lower, M, N, 0.7, A, M, B, M, 1.3, want, M)
+    ab.cblas_symm("d", ColMajor, Left, Lower, M, N, 0.7, A, M, B, M, 1.3, want, M)
     al, be = C.c_double(0.7), C.c_double(1.3)
     L.dsymm_(b"L", b"L", I(M), I(N), C.byref(al), vp(A), I(M), vp(B), I(M), C.byref(be), vp(got), I(M), C.c_size_t(1), C.c_size_t(1))
     assert np.array_equal(got, want)
     A = oracle.gegen("d", N, K, N, 4); B = oracle.gegen("d", N, K, N, 5); C0 = oracle.gegen("d", N, N, N, 6)
     want, got = C0.copy(order="F"), C0.copy(order="F")
-    ab.cblas_dsyr2k(ColMajor, Upper, NoTrans, N, K, 0.7, A, N, B, N, 1.3, want, N)
+    ab.cblas_syr2k("d", ColMajor, Upper, NoTrans, N, K, 0.7, A, N, B, N, 1.3, want, N)
     L.dsyr2k_(b"U", b"N", I(N), I(K), C.byref(al), vp(A), I(N), vp(B), I(N), C.byref(be), vp(got), I(N), C.c_size_t(1), C.c_size_t(1))
     assert np.array_equal(got, want)
     A = oracle.gegen("z", M, M, M, 7); B = oracle.gegen("z", M, N, M, 8); C0 = oracle.gegen("z", M, N, M, 9)
     want, got = C0.copy(order="F"), C0.copy(order="F")
     za = np.array([0.7 + 0.2j]); zb = np.array([1.3 - 0.1j])
-    ab.cblas_zhemm(ColMajor, Left, Upper, M, N, complex(za[0]), A, M, B, M, complex(zb[0]), want, M)
+    ab.cblas_hemm("z", ColMajor, Left, Upper, M, N, complex(za[0]), A, M, B, M, complex(zb[0]), want, M)
     L.zhemm_(b"L", b"U", I(M), I(N), vp(za), vp(A), I(M), vp(B), I(M), vp(zb), vp(got), I(M), C.c_size_t(1), C.c_size_t(1))
     assert np.array_equal(got, want)
     A = oracle.gegen("z", K, N, K, 10); B = oracle.gegen("z", K, N, K, 11); C0 = oracle.gegen("z", N, N, N, 12)
     want, got = C0.copy(order="F"), C0.copy(order="F")
-    ab.cblas_zher2k(ColMajor, Lower, ConjTrans, N, K, complex(za[0]), A, K, B, K, 1.3, want, N)
+    ab.cblas_her2k("z", ColMajor, Lower, ConjTrans, N, K, complex(za[0]), A, K, B, K, 1.3, want, N)
     rb = C.c_double(1.3)
     L.zher2k_(b"L", b"C", I(N), I(K), vp(za), vp(A), I(K), vp(B), I(K), C.byref(rb), vp(got), I(N), C.c_size_t(1), C.c_size_t(1))
     assert np.array_equal(got, want)
