@@ -116,8 +116,6 @@ dgemm_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                  double* __restrict__ C, size_t ldc, int M, int N, int K, double alpha, double beta,
                  int cmode, int tiles_m, int tiles_n, const int* abort_flag,
                  const SmMask reserved, int* tile_counter) {
-  const bool no_prefetch = (cmode & 0x100) != 0;    // debug bit (ATLB200_DEBUG_NO_CPREFETCH)
-  cmode &= 0xff;
   if (abort_flag && *abort_flag) return;  // POTRF stop-at-first-failure (uniform for the whole grid)
   {
     const unsigned sm = my_smid();
@@ -201,7 +199,7 @@ dgemm_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     int m0, n0;
     tile_coords(tile, tiles_m, tiles_n, m0, n0);
 
-    if (!beta0 && !no_prefetch) {
+    if (!beta0) {
       // bring this tile's C block (128 columns x 1 KiB) into L2 while the k loop runs: thread i of
       // the 256 consumers takes column i/2, half i%2, four 128-byte lines
       const int ctid = (int)threadIdx.x;               // consumer warps are 0..7
@@ -336,8 +334,6 @@ void launch(const CUtensorMap& ta, const CUtensorMap& tb, double* C, size_t ldc,
     AB_CUDA_CHECK(cudaFuncSetAttribute(dgemm_tma_kernel<AK, BK_>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
     attr_set = true;
   }
-  static const bool dbg_nopf = getenv("ATLB200_DEBUG_NO_CPREFETCH") != nullptr;
-  if (dbg_nopf) cmode |= 0x100;
   const int tiles_m = (M + BM - 1) / BM, tiles_n = (N + BN - 1) / BN;
   int grid = std::min(tiles_m * tiles_n, gemm_cta_cap());
   SmMask mask = {{0, 0, 0, 0}};

@@ -38,8 +38,6 @@ static void gemm_flags(int ta, int ca, int tb, int cb, int M, int N, int K, T al
     return;
   }
   if constexpr (std::is_same<T, double>::value) {
-    static const bool side_generic = getenv("ATLB200_DEBUG_SIDE_GENERIC") != nullptr;   // bisecting tool
-    if (side_generic && current_stream() != nullptr) { gemm_generic_launch(p); return; }
     if ((double)M * N * K >= 262144.0 && !herk &&
         dgemm_tma(ta, tb, M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, cmode, abort_flag))
       return;
