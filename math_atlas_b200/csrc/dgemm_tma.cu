@@ -359,6 +359,8 @@ void launch(const CUtensorMap& ta, const CUtensorMap& tb, double* C, size_t ldc,
 static thread_local int g_cta_cap = 0;
 int gemm_cta_cap() {
   if (g_cta_cap > 0) return g_cta_cap;
+  static const int env_cap = [] { const char* v = getenv("ATLB200_GEMM_CTA_CAP"); return v ? atoi(v) : 0; }();   // diagnostic: > #SMs = one tile per CTA
+  if (env_cap > 0) return env_cap;
   static int sms = 0;
   if (!sms) { int dev; AB_CUDA_CHECK(cudaGetDevice(&dev)); AB_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev)); }
   return sms;

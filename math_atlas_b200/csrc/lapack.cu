@@ -430,6 +430,36 @@ thread_local SideStream g_side;
 int env_int(const char* name, int dflt) { const char* v = getenv(name); return v ? atoi(v) : dflt; }
 }  // namespace
 
+// ---- diagnostic (ATLB200_LU_CHECKSUM=1): deterministic checksums of the regions a block step produces,
+// so that two runs on the same matrix can be compared step by step (tools/lu_stress.py prints the first
+// step and region that differ).  Fixed summation order: 256 CTAs x 256 threads, then one CTA.
+template <typename T>
+__global__ void __launch_bounds__(256) cks_partial_kernel(int rows, int cols, const T* A, size_t lda, double* part) {
+  __shared__ double sh[256];
+  double acc = 0.;
+  const long long total = (long long)rows * cols;
+  for (long long e = (long long)blockIdx.x * 256 + threadIdx.x; e < total; e += 256LL * gridDim.x) {
+    const T v = A[(size_t)(e % rows) + (size_t)(e / rows) * lda];
+    if constexpr (ST<T>::cplx) acc += (double)v.x * 1.0000001 + (double)v.y; else acc += (double)v * (1.0 + 1e-7 * (double)(e & 1023));
+  }
+  sh[threadIdx.x] = acc;
+  __syncthreads();
+  for (int s2 = 128; s2 > 0; s2 >>= 1) { if ((int)threadIdx.x < s2) sh[threadIdx.x] += sh[threadIdx.x + s2]; __syncthreads(); }
+  if (threadIdx.x == 0) part[blockIdx.x] = sh[0];
+}
+__global__ void cks_final_kernel(const double* part, int n, double* out) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) { double a = 0.; for (int i = 0; i < n; i++) a += part[i]; *out = a; }
+}
+static double* g_cks = nullptr;      // [step][3] on the device
+static int g_cks_steps = 0;
+template <typename T>
+static void lu_checksum(int slot, int rows, int cols, const T* A, size_t lda, int ws_slot = 2) {
+  if (!g_cks || rows <= 0 || cols <= 0) return;
+  double* part = static_cast<double*>(workspace(256 * sizeof(double), ws_slot));   // (the two streams use different scratch)
+  cks_partial_kernel<T><<<256, 256, 0, current_stream()>>>(rows, cols, A, lda, part);
+  cks_final_kernel<<<1, 32, 0, current_stream()>>>(part, 256, g_cks + slot);
+}
+
 template <typename T>
 static void lu_apply_panel(T* A, size_t lda, int M, int k0, int w, int c0, int nc, const int* d_ipiv) {
   // columns [c0, c0+nc) receive panel [k0, k0+w): interchanges, U block row, Schur complement
@@ -456,6 +486,13 @@ static void getrf_lookahead(int M, int N, T* A, size_t lda, int* d_ipiv, int* d_
   auto mark = [&](cudaStream_t st) { if (trace) { cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, st); tev.push_back(e); } };
   mark(U);
 
+  const bool cks = env_int("ATLB200_LU_CHECKSUM", 0) != 0;
+  if (cks) {
+    g_cks_steps = (MN + NB - 1) / NB;
+    if (g_cks) cudaFree(g_cks);
+    AB_CUDA_CHECK(cudaMalloc(&g_cks, sizeof(double) * 3 * (g_cks_steps + 1)));
+    AB_CUDA_CHECK(cudaMemsetAsync(g_cks, 0, sizeof(double) * 3 * (g_cks_steps + 1), U));
+  } else g_cks = nullptr;
   getrf_rec<T>(A, lda, 0, M, min(NB, N), d_ipiv, d_info);           // panel 0 on the main stream
   for (int k0 = 0, k = 0; k0 < MN; k0 += NB, k++) {
     const int w = min(NB, MN - k0);
@@ -477,11 +514,13 @@ static void getrf_lookahead(int M, int N, T* A, size_t lda, int* d_ipiv, int* d_
       }
       if (more) {
         lu_apply_panel<T>(A, lda, M, k0, w, c1, w1, d_ipiv);          // next panel's columns first
+        if (cks) lu_checksum<T>(3 * k, M, w1, A + (size_t)c1 * lda, lda);              // panel k+1 as the panel kernels will see it
         AB_CUDA_CHECK(cudaEventRecord(ss.cols[k & 1], U));
         AB_CUDA_CHECK(cudaStreamWaitEvent(P, ss.cols[k & 1], 0));
         set_current_stream(P);
         mark(P);
         getrf_rec<T>(A, lda, c1, M - c1, w1, d_ipiv, d_info);         // panel k+1 beside the update
+        if (cks) lu_checksum<T>(3 * k + 1, M, w1, A + (size_t)c1 * lda, lda, 7);       // ... and as they leave it (on P)
         mark(P);
         AB_CUDA_CHECK(cudaEventRecord(ss.panel[k & 1], P));
         set_current_stream(U);
@@ -511,6 +550,7 @@ static void getrf_lookahead(int M, int N, T* A, size_t lda, int* d_ipiv, int* d_
         continue;
       }
       lu_apply_panel<T>(A, lda, M, k0, w, c0, nc, d_ipiv);
+      if (cks && more && nc > 0) lu_checksum<T>(3 * k + 2, M, nc, A + (size_t)c0 * lda, lda);   // the rest columns after update k
       if (more) mark(U);
       set_gemm_reserved(nullptr);
     }
@@ -535,6 +575,13 @@ static void getrf_lookahead(int M, int N, T* A, size_t lda, int* d_ipiv, int* d_
 // long persistent update can always be scheduled.  n < 0: dynamic tile sharing only - for a rank whose
 // collective kernel is already resident: the GEMM CTAs it displaces start late and must not each
 // carry a full static share of the tiles.
+int lu_checksums(double* host_out, int max_steps) {
+  if (!g_cks) return 0;
+  const int n = g_cks_steps < max_steps ? g_cks_steps : max_steps;
+  AB_CUDA_CHECK(cudaMemcpy(host_out, g_cks, sizeof(double) * 3 * n, cudaMemcpyDeviceToHost));
+  return n;
+}
+
 void lu_reserve_sms(int n) {
   unsigned long long m[4] = {0, 0, 0, 0};
   if (n < 0) { set_gemm_reserved(m); return; }     // no SM kept free, but tiles are shared dynamically
