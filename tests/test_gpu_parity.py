@@ -342,3 +342,28 @@ def test_host_pointer_pipeline_matches_device_path(ta, tb):
     assert np.array_equal(got[n:], C0[n:]), "lda gap overwritten"
     err = np.max(np.abs(got[:n] - want[:n]))
     assert err < 64 * np.finfo(np.float64).eps * n * 0.25, err      # summation order differs (K chunks), nothing else
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("what", ["getrf", "potrf"])
+def test_factorisations_are_run_to_run_deterministic(what):
+    """The look-ahead drivers use two streams; pivots and factors must not depend on how the streams
+    interleave (tools/lu_stress.py is the long version of this test, profiles/r01_lu_stress.txt its history)."""
+    import torch
+    n = 4096
+    g = torch.Generator(device="cuda"); g.manual_seed(99)
+    A0 = torch.rand((n, n), device="cuda", dtype=torch.float64, generator=g) - 0.5
+    if what == "potrf":
+        A0 = A0 @ A0.T / n + 4.0 * torch.eye(n, device="cuda", dtype=torch.float64)
+    piv = torch.zeros(n, dtype=torch.int32, device="cuda")
+    ref = None
+    for it in range(8):
+        A = A0.clone()
+        info = ab.clapack_dgetrf(ColMajor, n, n, A, n, piv) if what == "getrf" else ab.clapack_dpotrf(ColMajor, Lower, n, A, n)
+        assert info == 0
+        cur = (A.clone(), piv.clone())
+        if ref is None:
+            ref = cur
+        else:
+            assert torch.equal(cur[1], ref[1]), f"{what}: pivots differ between runs (run {it})"
+            assert torch.equal(cur[0], ref[0]), f"{what}: factors differ between runs (run {it})"
