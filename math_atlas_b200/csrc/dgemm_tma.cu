@@ -329,9 +329,10 @@ constexpr int NCOUNTERS = 256;
 template <bool AK, bool BK_>
 void launch(const CUtensorMap& ta, const CUtensorMap& tb, double* C, size_t ldc, int M, int N, int K, double alpha,
             double beta, int cmode, const int* abort_flag) {
+  constexpr int smem_req = SMEM_BYTES;
   static bool attr_set = false;
   if (!attr_set) {
-    AB_CUDA_CHECK(cudaFuncSetAttribute(dgemm_tma_kernel<AK, BK_>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    AB_CUDA_CHECK(cudaFuncSetAttribute(dgemm_tma_kernel<AK, BK_>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_req));
     attr_set = true;
   }
   const int tiles_m = (M + BM - 1) / BM, tiles_n = (N + BN - 1) / BN;
@@ -347,7 +348,7 @@ void launch(const CUtensorMap& ta, const CUtensorMap& tb, double* C, size_t ldc,
     counter = g_counters + (g_counter_next++ % NCOUNTERS);
     AB_CUDA_CHECK(cudaMemsetAsync(counter, 0, sizeof(int), current_stream()));
   }
-  dgemm_tma_kernel<AK, BK_><<<grid, THREADS, SMEM_BYTES, current_stream()>>>(
+  dgemm_tma_kernel<AK, BK_><<<grid, THREADS, smem_req, current_stream()>>>(
       ta, tb, C, ldc, M, N, K, alpha, beta, cmode, tiles_m, tiles_n, abort_flag, mask, counter);
   count_launch();
   AB_CUDA_CHECK(cudaGetLastError());
