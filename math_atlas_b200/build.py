@@ -29,7 +29,23 @@ def _needs(obj, deps):
     return (not os.path.exists(obj)) or any(os.path.getmtime(d) > os.path.getmtime(obj) for d in deps)
 
 
-def build(force=False, verbose=False):
+def build(force=False, verbose=False, diag=False):
+    """diag=True builds tools/bin/libatlas_b200_diag.so with -DATLB200_DIAG (the look-ahead race
+    diagnostics of csrc/lu_diag.cuh); the product library never contains that code."""
+    global OBJ, LIB
+    if diag:
+        obj_prod, lib_prod = OBJ, LIB
+        OBJ = os.path.join(CSRC, "obj_diag")
+        LIB = os.path.join(os.path.dirname(HERE), "tools", "bin", "libatlas_b200_diag.so")
+        os.makedirs(os.path.dirname(LIB), exist_ok=True)
+        try:
+            return _build(force, verbose, ["-DATLB200_DIAG"])
+        finally:
+            OBJ, LIB = obj_prod, lib_prod
+    return _build(force, verbose, [])
+
+
+def _build(force, verbose, extra):
     os.makedirs(OBJ, exist_ok=True)
     headers = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".h", ".cuh"))]
     nvcc = os.environ.get("NVCC", "nvcc")
@@ -38,7 +54,7 @@ def build(force=False, verbose=False):
         s = os.path.join(CSRC, src)
         o = os.path.join(OBJ, src.replace(".cu", ".o"))
         if force or _needs(o, [s] + headers):
-            cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", s, "-o", o]
+            cmd = [nvcc] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + ["-c", s, "-o", o]
             r = subprocess.run(cmd, capture_output=True, text=True)
             if r.returncode != 0:
                 raise RuntimeError(f"nvcc failed for {src}:\n{r.stdout}\n{r.stderr}")
@@ -59,4 +75,4 @@ def build(force=False, verbose=False):
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv, diag="--diag" in sys.argv))

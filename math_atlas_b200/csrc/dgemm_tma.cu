@@ -50,6 +50,21 @@ __device__ __forceinline__ void mbar_expect_tx(uint32_t a, uint32_t bytes) {
 __device__ __forceinline__ void mbar_arrive(uint32_t a) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(a) : "memory");
 }
+// Consumer release of a pipeline stage (the WAR edge of the ring: generic-proxy ld.shared of the stage, then the
+// producer's TMA refill through the async proxy).  Two things are needed before the arrive on the "empty" barrier:
+//  * the loads must have RETURNED, not merely issued.  ptxas schedules SYNCS.ARRIVE straight after the last LDS
+//    with no scoreboard wait (it has no register dependency on them) and, when a co-resident CTA of another
+//    kernel keeps the SM's load/store pipe busy with uncoalesced global accesses (the LU look-ahead's laswp
+//    beside the trailing update), those last LDS instructions of a stage were observed to sample shared memory
+//    up to a microsecond later - after the last arriving warp had released the stage and the refill had landed:
+//    one A fragment (8 rows x 4 k) of one warp came from k-tile kt+STAGES, a 256-element error in C.
+//    `dep` carries the low words of the stage's last fragments ANDed with a run-time zero, so the arrive's
+//    address depends on every one of them and cannot issue before they are in registers;
+//  * fence.proxy.async orders the generic-proxy reads before the async-proxy writes that the arrive licenses.
+__device__ __forceinline__ void mbar_release(uint32_t a, uint32_t dep) {
+  asm volatile("fence.proxy.async.shared::cta;\n\tmbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(a + dep) : "memory");
+}
+__device__ __forceinline__ uint32_t lo32(double v) { return (uint32_t)__double2loint(v); }
 __device__ __forceinline__ void mbar_wait(uint32_t a, uint32_t parity) {
   uint32_t done;
   do {
@@ -185,6 +200,7 @@ dgemm_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   const uint32_t a_lane = A_KMAJOR ? (uint32_t)(wm * 64) * 128u + LK : (uint32_t)(wm * 4) * 2048u + LM;
   const uint32_t b_lane = B_KMAJOR ? (uint32_t)(wn * 32) * 128u + LK : (uint32_t)(wn * 2) * 2048u + LM;
   const bool beta0 = (beta == 0.);
+  const uint32_t zero_rt = (uint32_t)(ldc >> 63);   // 0 at run time, unknown to the compiler (see mbar_release)
 
   uint32_t it = 0;
   for (;;) {
@@ -222,6 +238,7 @@ dgemm_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       const uint32_t ph = (it / STAGES) & 1;
       if (kt > 0) mbar_wait(bar_base + 8 * s, ph);
       const uint32_t sa = smem_base + s * STAGE_BYTES, sb = sa + A_TILE_BYTES;
+      uint32_t dep = 0;
 #pragma unroll
       for (int j = 0; j < 4; j++) {
         double a[8], b[4];
@@ -238,13 +255,19 @@ dgemm_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                                         : (b_lane + (ni >> 1) * 2048u) ^ xm(j, ni & 1);
           b[ni] = lds_f64(sb + off);
         }
+        if (j == 3) {   // the loads of a warp return in order: the last group covers the stage
+#pragma unroll
+          for (int mi = 0; mi < 8; mi++) dep |= lo32(a[mi]);
+#pragma unroll
+          for (int ni = 0; ni < 4; ni++) dep |= lo32(b[ni]);
+        }
 #pragma unroll
         for (int mi = 0; mi < 8; mi++)
 #pragma unroll
           for (int ni = 0; ni < 4; ni++) dmma884(acc[mi][ni][0], acc[mi][ni][1], a[mi], b[ni]);
       }
       __syncwarp();
-      if (lane == 0) mbar_arrive(bar_base + 8 * (STAGES + s));
+      if (lane == 0) mbar_release(bar_base + 8 * (STAGES + s), dep & zero_rt);
     }
 
     // ---- epilogue: C = alpha*acc + beta*C (ablk2cmat, atlas-ammm.base:550), triangle mask for SYRK ----

@@ -21,11 +21,17 @@
 #include "ab_api.h"
 #include "lu_panel_cluster.cuh"
 #include "dgemm_tma.h"
+#ifdef ATLB200_DIAG
+#include "lu_diag.cuh"
+#include "gemm_generic.cuh"
+#endif
 #include <cfloat>
 #include <type_traits>
 #include <vector>
 
 namespace ab {
+
+namespace { int env_int(const char* name, int dflt) { const char* v = getenv(name); return v ? atoi(v) : dflt; } }
 
 // ------------------------------------------------------------------------------------- laswp
 // One thread per column.  Swaps must be applied in order, but a batch of 32 consecutive swaps whose
@@ -85,8 +91,134 @@ __global__ void __launch_bounds__(64) laswp_kernel(int N, T* A, size_t lda, int 
 template <typename T>
 void laswp(int N, T* A, size_t lda, int K1, int K2, const int* d_piv, int inci) {
   if (N <= 0 || K2 <= K1) return;
+#ifdef ATLB200_DIAG
+  if (diag::on_side() && (diag::pnop() & 2)) return;
+#endif
   const int threads = 64;
   laswp_kernel<T><<<(N + threads - 1) / threads, threads, 0, current_stream()>>>(N, A, lda, K1, K2, d_piv, inci);
+  count_launch();
+  AB_CUDA_CHECK(cudaGetLastError());
+}
+
+// ------------------------------------------------------------------------------------- fused interchange + unit-lower solve
+// One step of the right-looking panel factorisation (see getrf_panel below): after the leaf has factored the
+// b <= 32 columns starting at (row0, row0), the columns to its right need the b row interchanges and the solve
+// with the unit-lower triangle L11 (reference: ATL_laswp + cblas_trsm(Left,Lower,NoTrans,Unit) in ATL_getrfC,
+// atlas-lp.base:1548-1552), the columns to its left only the interchanges (:1561).  Both were separate
+// latency-bound launches (laswp_kernel is one thread per column walking the pivots in order, one 32-byte sector
+// per 8-byte element); here ONE kernel does all three for a block step:
+//   * warp 0 composes the b sequential swaps into a permutation (which original row ends in each of the b top
+//     positions, which original top row ends in each displaced pivot row) - content that enters the top block
+//     from below is final at once, so rows below the block only ever receive original top rows;
+//   * a CTA owns 64 columns, 4 threads per column (rows interleaved mod 4): all gathers are issued before any
+//     store, the displaced rows are written, the top block is solved in registers against L11 held in shared
+//     memory (column-oriented substitution, x[l] broadcast by shuffle) and written back;
+//   * CTAs past the right-hand columns serve the left-hand columns (interchanges only).
+template <typename T> __device__ __forceinline__ T pshfl(T v, int src);
+template <> __device__ __forceinline__ float pshfl<float>(float v, int src) { return __shfl_sync(0xffffffffu, v, src); }
+template <> __device__ __forceinline__ double pshfl<double>(double v, int src) { return __shfl_sync(0xffffffffu, v, src); }
+template <> __device__ __forceinline__ float2 pshfl<float2>(float2 v, int src) { return make_float2(__shfl_sync(0xffffffffu, v.x, src), __shfl_sync(0xffffffffu, v.y, src)); }
+template <> __device__ __forceinline__ double2 pshfl<double2>(double2 v, int src) { return make_double2(__shfl_sync(0xffffffffu, v.x, src), __shfl_sync(0xffffffffu, v.y, src)); }
+
+constexpr int SW_NB = 32;          // max pivots per step (the leaf width)
+constexpr int SW_COLS = 64, SW_Q = 4;
+
+template <typename T>
+__global__ void __launch_bounds__(SW_COLS * SW_Q)
+swap_trsm_kernel(T* A0, size_t lda, int row0, int b, const int* ipiv, int cR0, int nR, int cL0, int nL) {
+  using S = ST<T>;
+  constexpr int RP = SW_NB / SW_Q;
+  __shared__ T Lc[SW_NB][SW_NB + 1];        // Lc[l][i] = L11(i,l), i > l
+  __shared__ int top_src[SW_NB];            // original row whose content ends in top position i
+  __shared__ int out_row[SW_NB], out_src[SW_NB];   // displaced row below the block <- original (top) row
+  __shared__ int n_out;
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const int nRb = (nR + SW_COLS - 1) / SW_COLS;
+  const bool right = (int)blockIdx.x < nRb;
+  if (wid == 0) {
+    // lane i tracks top position i; lane k also tracks the k-th displaced row found so far
+    int cur = row0 + lane;                  // original row now at top position `lane`
+    int orow = -1, ocur = -1, cnt = 0;
+    const int myp = (lane < b) ? ipiv[row0 + lane] : -1;
+    for (int i = 0; i < b; i++) {
+      const int p = __shfl_sync(0xffffffffu, myp, i);
+      const int ci = __shfl_sync(0xffffffffu, cur, i);
+      if (p == row0 + i) continue;                       // uniform
+      if (p < row0 + b) {                                // target inside the top block
+        const int cp = __shfl_sync(0xffffffffu, cur, p - row0);
+        if (lane == i) cur = cp;
+        if (lane == p - row0) cur = ci;
+      } else {
+        const unsigned hit = __ballot_sync(0xffffffffu, orow == p);
+        int k;
+        if (hit) k = __ffs(hit) - 1;
+        else { k = cnt; if (lane == k) { orow = p; ocur = p; } cnt++; }
+        const int co = __shfl_sync(0xffffffffu, ocur, k);
+        if (lane == i) cur = co;
+        if (lane == k) ocur = ci;
+      }
+    }
+    top_src[lane] = cur;
+    out_row[lane] = orow; out_src[lane] = ocur;
+    if (lane == 0) n_out = cnt;
+  } else if (right) {
+    // L11 (strictly lower part) -> shared memory, transposed access Lc[l][i]
+    for (int idx = tid - 32; idx < SW_NB * SW_NB; idx += SW_COLS * SW_Q - 32) {
+      const int i = idx % SW_NB, l = idx / SW_NB;
+      T v = S::zero();
+      if (i < b && l < i) v = A0[(size_t)(row0 + i) + (size_t)(row0 + l) * lda];
+      Lc[l][i] = v;
+    }
+  }
+  __syncthreads();
+  const int q = tid & (SW_Q - 1), grp = tid >> 2;
+  int col; bool live;
+  if (right) { const int v = blockIdx.x * SW_COLS + grp; live = v < nR; col = cR0 + v; }
+  else { const int v = ((int)blockIdx.x - nRb) * SW_COLS + grp; live = v < nL; col = cL0 + v; }
+  T* bp = A0 + (size_t)(live ? col : cR0) * lda;
+  const int nout = n_out;
+  T x[RP], o[RP];
+#pragma unroll
+  for (int m = 0; m < RP; m++) {
+    const int i = m * SW_Q + q;
+    x[m] = S::zero(); o[m] = S::zero();
+    if (live && i < b) x[m] = bp[top_src[i]];
+    if (live && i < nout) o[m] = bp[out_src[i]];
+  }
+  __syncwarp();        // the 4 threads of a column are in one warp: every gather precedes every store
+#pragma unroll
+  for (int m = 0; m < RP; m++) {
+    const int i = m * SW_Q + q;
+    if (live && i < nout) bp[out_row[i]] = o[m];
+  }
+  if (right) {
+    const int lane_base = lane & ~(SW_Q - 1);
+#pragma unroll
+    for (int l = 0; l < SW_NB; l++) {
+      if (l < b) {                                       // uniform
+        const T xl = pshfl<T>(x[l / SW_Q], lane_base + (l % SW_Q));
+#pragma unroll
+        for (int m = l / SW_Q; m < RP; m++) {
+          const int i = m * SW_Q + q;
+          if (i > l) x[m] = S::sub(x[m], S::mul(Lc[l][i], xl));
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int m = 0; m < RP; m++) {
+    const int i = m * SW_Q + q;
+    if (live && i < b) bp[row0 + i] = x[m];
+  }
+}
+
+template <typename T>
+static void swap_trsm(T* A0, size_t lda, int row0, int b, const int* d_ipiv, int cR0, int nR, int cL0, int nL) {
+  if (nR < 0) nR = 0;
+  if (nL < 0) nL = 0;
+  const int grid = (nR + SW_COLS - 1) / SW_COLS + (nL + SW_COLS - 1) / SW_COLS;
+  if (grid == 0 || b <= 0) return;
+  swap_trsm_kernel<T><<<grid, SW_COLS * SW_Q, 0, current_stream()>>>(A0, lda, row0, b, d_ipiv, cR0, nR, cL0, nL);
   count_launch();
   AB_CUDA_CHECK(cudaGetLastError());
 }
@@ -350,6 +482,9 @@ template <typename T>
 static int leaf_width_for(int M, bool* use_cluster) {
   constexpr int E = PanelW<T>::W;
   *use_cluster = true;
+#ifdef ATLB200_DIAG
+  if (diag::nocluster_on()) { *use_cluster = false; return panel_width_for<T>(M); }
+#endif
   if (M <= cluster_capacity<T, E, 1>()) return E;
   if (M <= cluster_capacity<T, E / 2, 2>()) return E / 2;
   // (an E/4-wide cluster leaf would hold 4x the rows, but measured slower than the global-barrier
@@ -361,10 +496,58 @@ static int leaf_width_for(int M, bool* use_cluster) {
 template <typename T>
 static void getf2_leaf(int M, int w, int lw, bool use_cluster, T* A, size_t lda, int* d_ipiv, int* d_info, int piv_off, int info_off) {
   constexpr int E = PanelW<T>::W;
+#ifdef ATLB200_DIAG
+  if (diag::on_side() && (diag::pnop() & (1 | 16 | 32))) {
+    // stand-in for the leaf: identity pivots, optionally a kernel of the leaf's launch shape that touches no global memory
+    const int mn = min(M, w), bits = diag::pnop();
+    diag::ident_piv_kernel<<<(mn + 127) / 128, 128, 0, current_stream()>>>(d_ipiv, mn, piv_off);
+    if (bits & (16 | 32)) {
+      int c = 1; while (c * CL_TPB * (32 / lw) < M) c <<= 1;
+      cudaLaunchConfig_t cfg{};
+      cfg.gridDim = dim3(c); cfg.blockDim = dim3(512); cfg.stream = current_stream();
+      cudaLaunchAttribute at[1];
+      at[0].id = cudaLaunchAttributeClusterDimension;
+      at[0].val.clusterDim.x = (bits & 16) ? c : 1; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+      cfg.attrs = at; cfg.numAttrs = 1;
+      static bool attr = false;
+      if (!attr) { (void)cudaFuncSetAttribute(diag::spin_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1); attr = true; }
+      AB_CUDA_CHECK(cudaLaunchKernelEx(&cfg, diag::spin_kernel, (long long)(3000LL * w), (bits & 16) ? 1 : 0));
+    }
+    return;
+  }
+#endif
   if (!use_cluster) { getf2_panel<T>(M, w, lw, A, lda, d_ipiv, d_info, piv_off, info_off); return; }
   if (lw == E) cluster_launch<T, E, 1>(M, w, A, lda, d_ipiv, d_info, piv_off, info_off);
   else if (lw == E / 2) cluster_launch<T, E / 2, 2>(M, w, A, lda, d_ipiv, d_info, piv_off, info_off);
   else cluster_launch<T, E / 4, 4>(M, w, A, lda, d_ipiv, d_info, piv_off, info_off);
+}
+
+// ---- right-looking panel: leaf / fused interchange+solve / rank-b update ---------------------------------------
+// Factor the M x w panel (w <= a few hundred columns) whose top-left corner is (r0, r0) of A0.  The reference
+// recurses down to single columns (ATL_getrfC -> LU2/getf2, atlas-lp.base:1497-1617, 1301); on the GPU every
+// recursion node is a handful of latency-bound launches (interchanges, small solves, skinny GEMMs: ~90-160 per
+// 512-column panel, 2.8-6 ms).  Here the panel advances by the leaf width b (32 columns, 16 for tall panels / z):
+//   leaf (b columns, whole height, on-chip)  ->  swap_trsm (interchanges left and right, U12)  ->  rank-b update
+// three launches per b columns, and every element of the panel is touched by coalesced or TMA accesses only.
+// Arithmetic per column is that of getf2 on the updated column either way; pivots stay those of partial pivoting.
+template <typename T>
+static void getrf_panel(T* A0, size_t lda, int r0, int M, int w, int* d_ipiv, int* d_info) {
+  using S = ST<T>;
+  const int MN = min(M, w);
+  if (MN <= 0) return;
+  bool use_cluster;
+  const int lw = leaf_width_for<T>(M, &use_cluster);
+  for (int jb = 0; jb < MN; jb += lw) {
+    const int b = min(lw, MN - jb);
+    const int d = r0 + jb;                       // diagonal position of this block
+    T* Ad = A0 + (size_t)d + (size_t)d * lda;
+    getf2_leaf<T>(M - jb, b, lw, use_cluster, Ad, lda, d_ipiv + d, d_info, d, d);
+    const int nR = w - jb - b;                   // panel columns right of the block
+    swap_trsm<T>(A0, lda, d, b, d_ipiv, d + b, nR, r0, jb);
+    if (nR > 0 && M - jb - b > 0)
+      gemm<T>(NoTrans, NoTrans, M - jb - b, nR, b, S::from_real(-1), Ad + b, lda, Ad + (size_t)b * lda, lda, S::one(),
+              Ad + b + (size_t)b * lda, lda);
+  }
 }
 
 // Factor the M x N block whose top-left corner is (r0, r0) of the matrix A0.  Pivot indices and
@@ -379,8 +562,11 @@ static void getrf_rec(T* A0, size_t lda, int r0, int M, int N, int* d_ipiv, int*
   T* A = A0 + (size_t)r0 + (size_t)r0 * lda;
   bool use_cluster;
   const int leaf_w = leaf_width_for<T>(M, &use_cluster);
-  if (N <= leaf_w) {
-    getf2_leaf<T>(M, N, leaf_w, use_cluster, A, lda, d_ipiv + r0, d_info, r0, r0);
+  // nodes up to ATLB200_LU_PW columns are factored right-looking by getrf_panel (3 launches per leaf width);
+  // above that the reference's recursion keeps the updates as large-K GEMMs
+  static const int pw = env_int("ATLB200_LU_PW", 128);
+  if (N <= max(leaf_w, pw)) {
+    getrf_panel<T>(A0, lda, r0, M, N, d_ipiv, d_info);
     return;
   }
   // Nleft = MN/2 rounded down to a multiple of the leaf width (the reference rounds to its tuned
@@ -410,7 +596,6 @@ static void getrf_rec(T* A0, size_t lda, int r0, int M, int N, int* d_ipiv, int*
 // while the main stream applies update k to the rest of the trailing matrix.  Pivoting is
 // unchanged (the same column-by-column search on the same updated values).
 namespace {
-int env_int(const char* name, int dflt);
 struct SideStream {
   cudaStream_t st = nullptr;
   cudaEvent_t cols[2] = {nullptr, nullptr}, panel[2] = {nullptr, nullptr};
@@ -427,7 +612,6 @@ struct SideStream {
   }
 };
 thread_local SideStream g_side;
-int env_int(const char* name, int dflt) { const char* v = getenv(name); return v ? atoi(v) : dflt; }
 }  // namespace
 
 // ---- diagnostic (ATLB200_LU_CHECKSUM=1): deterministic checksums of the regions a block step produces,
@@ -472,6 +656,89 @@ static void lu_apply_panel(T* A, size_t lda, int M, int k0, int w, int c0, int n
             A + (size_t)k0 + (size_t)c0 * lda, lda, S::one(), A + (size_t)(k0 + w) + (size_t)c0 * lda, lda);
 }
 
+#ifdef ATLB200_DIAG
+template <typename T>
+struct DiagRun {
+  bool on = false, pending = false;
+  int steps = 0, tiles_cap = 0, cur = -1;
+  T* S = nullptr; size_t lds = 0;
+  unsigned long long* d_cks = nullptr; int* d_nbad = nullptr; int* d_tiles = nullptr; diag::Rec* d_recs = nullptr;
+  struct Step { int k, rows, cols, w; const T* A21; const T* U12; const T* C; size_t lda; };
+  std::vector<Step> log;
+  void init(int M, int N, int NB) {
+    on = diag::verify_on() != 0;
+    if (!on) return;
+    steps = (min(M, N) + NB - 1) / NB + 1;
+    lds = ((size_t)M + 15) & ~(size_t)15;
+    tiles_cap = ((M + 127) / 128) * ((N + 127) / 128);
+    AB_CUDA_CHECK(cudaMalloc(&S, sizeof(T) * lds * (size_t)N));
+    AB_CUDA_CHECK(cudaMalloc(&d_cks, sizeof(unsigned long long) * 5 * steps));
+    AB_CUDA_CHECK(cudaMalloc(&d_nbad, sizeof(int) * steps));
+    AB_CUDA_CHECK(cudaMalloc(&d_tiles, sizeof(int) * (size_t)tiles_cap * steps));
+    AB_CUDA_CHECK(cudaMalloc(&d_recs, sizeof(diag::Rec) * diag::MAXREC * steps));
+    AB_CUDA_CHECK(cudaMemset(d_cks, 0, sizeof(unsigned long long) * 5 * steps));
+    AB_CUDA_CHECK(cudaMemset(d_nbad, 0, sizeof(int) * steps));
+    AB_CUDA_CHECK(cudaMemset(d_tiles, 0, sizeof(int) * (size_t)tiles_cap * steps));
+    AB_CUDA_CHECK(cudaDeviceSynchronize());
+  }
+  void before(int k, int rows, int cols, int w, const T* A21, const T* U12, const T* C, size_t lda, cudaStream_t st) {
+    cur = (int)log.size();
+    log.push_back({k, rows, cols, w, A21, U12, C, lda});
+    diag::cks_kernel<T><<<64, 256, 0, st>>>(rows, w, A21, lda, d_cks + 5 * cur + 0);
+    diag::cks_kernel<T><<<64, 256, 0, st>>>(w, cols, U12, lda, d_cks + 5 * cur + 1);
+    diag::cks_kernel<T><<<64, 256, 0, st>>>(rows, cols, C, lda, d_cks + 5 * cur + 2);
+    diag::copy_kernel<T><<<296, 256, 0, st>>>(rows, cols, C, lda, S, lds);
+  }
+  void after(cudaStream_t st) {
+    pending = false;
+    const Step& s = log[cur];
+    using SS = ST<T>;
+    diag::cks_kernel<T><<<64, 256, 0, st>>>(s.rows, s.w, s.A21, s.lda, d_cks + 5 * cur + 3);
+    diag::cks_kernel<T><<<64, 256, 0, st>>>(s.w, s.cols, s.U12, s.lda, d_cks + 5 * cur + 4);
+    if (diag::pnop() & 64) {
+      GemmP<T> gp{s.rows, s.cols, s.w, s.A21, s.lda, 0, 0, s.U12, s.lda, 0, 0, SS::from_real(-1), SS::one(), S, lds, C_FULL, 0, 0, 0, nullptr};
+      gemm_generic_launch(gp);
+    } else
+      gemm<T>(NoTrans, NoTrans, s.rows, s.cols, s.w, SS::from_real(-1), s.A21, s.lda, s.U12, s.lda, SS::one(), S, lds);
+    diag::cmp_kernel<T><<<296, 256, 0, st>>>(s.rows, s.cols, s.C, s.lda, S, lds, d_nbad + cur, d_tiles + (size_t)cur * tiles_cap,
+                                              (s.rows + 127) / 128, d_recs + (size_t)cur * diag::MAXREC);
+  }
+  void report() {
+    if (!on) return;
+    AB_CUDA_CHECK(cudaDeviceSynchronize());
+    const int n = (int)log.size();
+    std::vector<unsigned long long> cks(5 * (size_t)steps);
+    std::vector<int> nbad(steps), tiles((size_t)tiles_cap * steps);
+    std::vector<diag::Rec> recs((size_t)diag::MAXREC * steps);
+    AB_CUDA_CHECK(cudaMemcpy(cks.data(), d_cks, cks.size() * 8, cudaMemcpyDeviceToHost));
+    AB_CUDA_CHECK(cudaMemcpy(nbad.data(), d_nbad, nbad.size() * 4, cudaMemcpyDeviceToHost));
+    AB_CUDA_CHECK(cudaMemcpy(tiles.data(), d_tiles, tiles.size() * 4, cudaMemcpyDeviceToHost));
+    AB_CUDA_CHECK(cudaMemcpy(recs.data(), d_recs, recs.size() * sizeof(diag::Rec), cudaMemcpyDeviceToHost));
+    int bad_steps = 0, late = 0;
+    for (int i = 0; i < n; i++) {
+      const bool lateA = cks[5 * i + 0] != cks[5 * i + 3], lateB = cks[5 * i + 1] != cks[5 * i + 4];
+      if (lateA || lateB) late++;
+      if (!nbad[i] && !lateA && !lateB) continue;
+      bad_steps++;
+      const Step& s = log[i];
+      const int tm = (s.rows + 127) / 128, tn = (s.cols + 127) / 128;
+      fprintf(stderr, "DIAG step %d (update %d x %d, k=%d): mismatching elements %d%s%s\n", s.k, s.rows, s.cols, s.w, nbad[i],
+              lateA ? "  [A21 CHANGED during the update]" : "", lateB ? "  [U12 CHANGED during the update]" : "");
+      int shown = 0;
+      for (int t = 0; t < tm * tn && shown < 24; t++)
+        if (tiles[(size_t)i * tiles_cap + t]) { fprintf(stderr, "   tile (%d,%d): %d\n", t % tm, t / tm, tiles[(size_t)i * tiles_cap + t]); shown++; }
+      for (int r = 0; r < min(nbad[i], diag::MAXREC) && r < 12; r++) {
+        const diag::Rec& q = recs[(size_t)i * diag::MAXREC + r];
+        double g, e; memcpy(&g, &q.got, 8); memcpy(&e, &q.exp, 8);
+        fprintf(stderr, "   (%d,%d) got % .17g  recomputed % .17g  diff % .3e\n", q.row, q.col, g, e, g - e);
+      }
+    }
+    fprintf(stderr, "DIAG summary: %d verified update steps, %d with mismatches or late writes, %d with late writes\n", n, bad_steps, late);
+    cudaFree(S); cudaFree(d_cks); cudaFree(d_nbad); cudaFree(d_tiles); cudaFree(d_recs);
+  }
+};
+#endif
+
 template <typename T>
 static void getrf_lookahead(int M, int N, T* A, size_t lda, int* d_ipiv, int* d_info, int NB) {
   const int MN = min(M, N);
@@ -486,6 +753,10 @@ static void getrf_lookahead(int M, int N, T* A, size_t lda, int* d_ipiv, int* d_
   auto mark = [&](cudaStream_t st) { if (trace) { cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, st); tev.push_back(e); } };
   mark(U);
 
+#ifdef ATLB200_DIAG
+  DiagRun<T> dg;
+  dg.init(M, N, NB);
+#endif
   const bool cks = env_int("ATLB200_LU_CHECKSUM", 0) != 0;
   if (cks) {
     g_cks_steps = (MN + NB - 1) / NB;
@@ -493,7 +764,7 @@ static void getrf_lookahead(int M, int N, T* A, size_t lda, int* d_ipiv, int* d_
     AB_CUDA_CHECK(cudaMalloc(&g_cks, sizeof(double) * 3 * (g_cks_steps + 1)));
     AB_CUDA_CHECK(cudaMemsetAsync(g_cks, 0, sizeof(double) * 3 * (g_cks_steps + 1), U));
   } else g_cks = nullptr;
-  getrf_rec<T>(A, lda, 0, M, min(NB, N), d_ipiv, d_info);           // panel 0 on the main stream
+  getrf_rec<T>(A, lda, 0, M, min(NB, N), d_ipiv, d_info);          // panel 0 on the main stream
   for (int k0 = 0, k = 0; k0 < MN; k0 += NB, k++) {
     const int w = min(NB, MN - k0);
     const int c1 = k0 + w;                       // first column right of the panel
@@ -519,7 +790,13 @@ static void getrf_lookahead(int M, int N, T* A, size_t lda, int* d_ipiv, int* d_
         AB_CUDA_CHECK(cudaStreamWaitEvent(P, ss.cols[k & 1], 0));
         set_current_stream(P);
         mark(P);
-        getrf_rec<T>(A, lda, c1, M - c1, w1, d_ipiv, d_info);         // panel k+1 beside the update
+#ifdef ATLB200_DIAG
+        diag::on_side() = true;
+#endif
+        getrf_rec<T>(A, lda, c1, M - c1, w1, d_ipiv, d_info);        // panel k+1 beside the update
+#ifdef ATLB200_DIAG
+        diag::on_side() = false;
+#endif
         if (cks) lu_checksum<T>(3 * k + 1, M, w1, A + (size_t)c1 * lda, lda, 7);       // ... and as they leave it (on P)
         mark(P);
         AB_CUDA_CHECK(cudaEventRecord(ss.panel[k & 1], P));
@@ -549,6 +826,25 @@ static void getrf_lookahead(int M, int N, T* A, size_t lda, int* d_ipiv, int* d_
         mark(U);
         continue;
       }
+#ifdef ATLB200_DIAG
+      if (dg.on && more && nc > 0 && M - k0 - w > 0) {
+        using S = ST<T>;
+        const int rows = M - k0 - w;
+        const T* A21 = A + (size_t)(k0 + w) + (size_t)k0 * lda;
+        T* U12 = A + (size_t)k0 + (size_t)c0 * lda;
+        T* C22 = A + (size_t)(k0 + w) + (size_t)c0 * lda;
+        laswp<T>(nc, A + (size_t)c0 * lda, lda, k0, k0 + w, d_ipiv, 1);
+        trsm<T>(Left, Lower, NoTrans, Unit, w, nc, S::one(), A + (size_t)k0 + (size_t)k0 * lda, lda, U12, lda);
+        dg.before(k, rows, nc, w, A21, U12, C22, lda, U);
+        if (diag::usync_on()) AB_CUDA_CHECK(cudaStreamSynchronize(U));
+        if (diag::pnop() & 64) {
+          GemmP<T> gp{rows, nc, w, A21, lda, 0, 0, U12, lda, 0, 0, S::from_real(-1), S::one(), C22, lda, C_FULL, 0, 0, 0, nullptr};
+          gemm_generic_launch(gp);
+        } else
+          gemm<T>(NoTrans, NoTrans, rows, nc, w, S::from_real(-1), A21, lda, U12, lda, S::one(), C22, lda);
+        dg.pending = true;
+      } else
+#endif
       lu_apply_panel<T>(A, lda, M, k0, w, c0, nc, d_ipiv);
       if (cks && more && nc > 0) lu_checksum<T>(3 * k + 2, M, nc, A + (size_t)c0 * lda, lda);   // the rest columns after update k
       if (more) mark(U);
@@ -556,7 +852,13 @@ static void getrf_lookahead(int M, int N, T* A, size_t lda, int* d_ipiv, int* d_
     }
     if (k0 > 0) laswp<T>(k0, A, lda, k0, k0 + w, d_ipiv, 1);           // interchanges left of the panel
     if (more && nright > 0) AB_CUDA_CHECK(cudaStreamWaitEvent(U, ss.panel[k & 1], 0));
+#ifdef ATLB200_DIAG
+    if (dg.pending) { set_gemm_reserved(nullptr); dg.after(U); }
+#endif
   }
+#ifdef ATLB200_DIAG
+  dg.report();
+#endif
   if (trace) {
     AB_CUDA_CHECK(cudaDeviceSynchronize());
     fprintf(stderr, "# getrf look-ahead trace M=%d N=%d NB=%d: step, panel(k+1) start..end [ms], update(rest) start..end [ms]\n", M, N, NB);

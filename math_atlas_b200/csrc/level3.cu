@@ -14,6 +14,9 @@
 #include "dgemm_tma.h"
 #include "zgemm_tma.h"
 #include "sgemm_ffma.h"
+#ifdef ATLB200_DIAG
+#include "lu_diag.cuh"
+#endif
 #include <cstdlib>
 #include <type_traits>
 
@@ -28,6 +31,9 @@ static void gemm_flags(int ta, int ca, int tb, int cb, int M, int N, int K, T al
                        size_t ldb, T beta, T* C, size_t ldc, int cmode, int herk, const int* abort_flag) {
   using S = ST<T>;
   if (M <= 0 || N <= 0) return;
+#ifdef ATLB200_DIAG
+  if (diag::on_side() && (diag::pnop() & 8)) return;
+#endif
   GemmP<T> p{M, N, K, A, lda, ta, S::cplx ? ca : 0, B, ldb, tb, S::cplx ? cb : 0, alpha, beta, C, ldc, cmode, herk, 0, 0, abort_flag};
   if (S::is_zero(alpha) || K <= 0) {
     // C <- beta*C only; beta==0 writes explicit zeros, A and B are not referenced
@@ -286,6 +292,9 @@ template <typename T>
 static void trsm_base(int side, int uplo, int trans, int diag, int M, int N, T alpha, const T* A, size_t lda, T* B,
                       size_t ldb, const int* abort_flag) {
   using S = ST<T>;
+#ifdef ATLB200_DIAG
+  if (diag::on_side() && (diag::pnop() & 4)) return;
+#endif
   const int left = (side == Left);
   const int n = left ? M : N, nvec = left ? N : M;
   const int tt = left ? is_tr(trans) : !is_tr(trans);

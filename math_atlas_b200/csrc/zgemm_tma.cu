@@ -42,6 +42,11 @@ __device__ __forceinline__ void mbar_expect_tx(uint32_t a, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(a), "r"(bytes) : "memory");
 }
 __device__ __forceinline__ void mbar_arrive(uint32_t a) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(a) : "memory"); }
+// consumer release of a stage: the ld.shared of the stage must have returned and be ordered before the TMA refill
+// (async proxy) that the arrive licenses - see mbar_release in dgemm_tma.cu for the failure this prevents
+__device__ __forceinline__ void mbar_release(uint32_t a, uint32_t dep) {
+  asm volatile("fence.proxy.async.shared::cta;\n\tmbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(a + dep) : "memory");
+}
 __device__ __forceinline__ void mbar_wait(uint32_t a, uint32_t parity) {
   uint32_t done;
   do {
@@ -138,6 +143,7 @@ zgemm_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   }
   const double sa_im = conjA ? -1.0 : 1.0, sb_im = conjB ? -1.0 : 1.0;
   const bool beta0 = (beta.x == 0. && beta.y == 0.);
+  const uint32_t zero_rt = (uint32_t)(ldc >> 63);   // 0 at run time, unknown to the compiler (see mbar_release)
 
   uint32_t it = 0;
   for (;;) {
@@ -158,6 +164,7 @@ zgemm_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       const uint32_t s = it % STAGES;
       if (kt > 0) mbar_wait(bar_base + 8 * s, (it / STAGES) & 1);
       const uint32_t sa = smem_base + s * STAGE_BYTES, sb = sa + A_TILE_BYTES;
+      uint32_t dep = 0;
 #pragma unroll
       for (int j = 0; j < 2; j++) {
         double ar[4], ai[4], nai[4], br[4], bi[4];
@@ -169,7 +176,12 @@ zgemm_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 #pragma unroll
         for (int ni = 0; ni < 4; ni++) {
           lds_z(sb + b_off[j] + ni * 1024u, br[ni], bi[ni]);
+          if (j == 1) dep |= (uint32_t)__double2loint(br[ni]);
           bi[ni] *= sb_im;
+        }
+        if (j == 1) {
+#pragma unroll
+          for (int mi = 0; mi < 4; mi++) dep |= (uint32_t)__double2loint(ar[mi]);
         }
 #pragma unroll
         for (int mi = 0; mi < 4; mi++)
@@ -182,7 +194,7 @@ zgemm_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           }
       }
       __syncwarp();
-      if (lane == 0) mbar_arrive(bar_base + 8 * (STAGES + s));
+      if (lane == 0) mbar_release(bar_base + 8 * (STAGES + s), dep & zero_rt);
     }
 
     // ---- epilogue: C = alpha*acc + beta*C (complex), triangle mask, HERK real diagonal ----

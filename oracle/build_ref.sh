@@ -29,7 +29,7 @@ rm -rf "$W"; mkdir -p "$W"; cd "$W"
 gcc -O2 -w -o xextract "$REF/extract.c" 2>/dev/null
 ./xextract -langM -b "$REF/AtlasBase/make.base" -o Makefile rout=Make.atldir \
     -def topd "$REF/AtlasBase" -def ext "$W/xextract" > /dev/null 2>&1
-make ATLAS ATLAS/include ATLAS/src ATLAS/src/testing ATLAS/src/lapack ATLAS/src/blas ATLAS/src/auxil \
+make ATLAS ATLAS/include ATLAS/bin ATLAS/src ATLAS/src/testing ATLAS/src/lapack ATLAS/src/blas ATLAS/src/auxil \
      ATLAS/src/blas/reference ATLAS/src/blas/reference/level1 ATLAS/src/blas/reference/level2 \
      ATLAS/src/blas/reference/level3 > extract.log 2>&1
 A=$W/ATLAS
@@ -64,5 +64,38 @@ gcc $CF -DDREAL -c $A/src/testing/ATL_rand.c -o obj/ATL_rand.o
 gcc $CF -DSCPLX -c $A/src/lapack/ATL_lapy2.c -o obj/c_lapy2.o
 gcc $CF -DDCPLX -c $A/src/lapack/ATL_lapy2.c -o obj/z_lapy2.o
 gcc -shared -o "$OUT/libatlref.so" obj/*.o -lm
+
+# 3. The reference's own tester PROGRAMS (bin/l3blastst.c, lutst.c, llttst.c, trtritst.c, uumtst.c, invtst.c;
+#    AtlasBase/Antoine/atlbinblas.base:11055-15340, Clint/atlas-tlp.base) compiled unmodified with
+#    -DUSE_L3_REFERENCE (trusted BLAS = the reference triple loops) and linked against OUR library first:
+#    every ATL_X{gemm,syrk,...,getrf,potrf,laswp} / cblas_* / clapack_* call of a tester binds to
+#    math_atlas_b200/libatlas_b200.so; generators, norms and the trusted ATL_Xref* come from libatlref.so;
+#    oracle/ref_shim/tester_shim.c (ours) supplies what a tuned build would (see its header).
+#    BASELINE config 1 ("cblas_dgemm M=N=K=2000 ... checked by ATLAS xdl3blastst") is tests/test_ref_testers.py.
+LIB200=$(cd "$HERE/../math_atlas_b200" && pwd)
+if [ -f "$LIB200/libatlas_b200.so" ]; then
+  mkdir -p tobj "$OUT/bin"
+  TF="$CF -DL2SIZE=4194304 -DUSE_L3_REFERENCE"
+  for t in s:SREAL d:DREAL c:SCPLX z:DCPLX; do
+    p=${t%%:*}; D=${t##*:}
+    X=""; [ $p = d ] && X=-DSHIM_COMMON
+    gcc $TF -D$D $X -c $HERE/ref_shim/tester_shim.c -o tobj/shim_$p.o
+    for f in ATL_gecmpBV ATL_trcmpBV; do gcc $TF -D$D -c $A/src/testing/$f.c -o tobj/bv_${p}_$f.o; done
+  done
+  for f in $A/src/testing/ATL_print2dBV.c $A/src/testing/ATL_print1dBV.c $A/src/auxil/ATL_*BV.c; do
+    gcc $TF -DDREAL -c $f -o tobj/bv_$(basename $f .c).o
+  done
+  for t in s:SREAL d:DREAL c:SCPLX z:DCPLX; do
+    p=${t%%:*}; D=${t##*:}
+    for x in l3blastst lutst llttst trtritst uumtst invtst; do
+      gcc $TF -D$D -c $A/bin/$x.c -o tobj/$p$x.o
+      gcc -o "$OUT/bin/x$p$x" tobj/$p$x.o tobj/shim_*.o tobj/bv_*.o -L"$LIB200" -latlas_b200 -L"$OUT" -latlref -lm \
+          -Wl,-rpath,'$ORIGIN/../../../math_atlas_b200' -Wl,-rpath,'$ORIGIN/..'
+    done
+  done
+  echo "build_ref: built $(ls $OUT/bin | wc -l) tester programs in $OUT/bin"
+else
+  echo "build_ref: libatlas_b200.so not built yet - tester programs skipped"
+fi
 cd "$HERE"; rm -rf "$W"
 echo "build_ref: built $OUT/libatlref.so"

@@ -42,7 +42,8 @@ def build_oracle(force=False):
 def build_ref():
     """Build oracle/_ref/libatlref.so if /root/reference is present; returns path or None."""
     so = os.path.join(HERE, "_ref", "libatlref.so")
-    if not os.path.exists(so) and os.path.exists("/root/reference/extract.c"):
+    testers = os.path.join(HERE, "_ref", "bin", "xdl3blastst")   # the reference's tester programs linked to our library
+    if (not os.path.exists(so) or not os.path.exists(testers)) and os.path.exists("/root/reference/extract.c"):
         subprocess.check_call(["bash", os.path.join(HERE, "build_ref.sh")])
     return so if os.path.exists(so) else None
 
