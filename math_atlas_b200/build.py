@@ -16,45 +16,61 @@ OBJ = os.path.join(CSRC, "obj")
 LIB = os.path.join(HERE, "libatlas_b200.so")
 SOURCES = ["runtime.cu", "dgemm_tma.cu", "zgemm_tma.cu", "sgemm_ffma.cu", "sgemm_tc.cu", "cgemm_ffma.cu", "level3.cu", "lapack.cu", "lapack_inv.cu", "capi.cu", "probe.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC",
-              "--expt-relaxed-constexpr", "-diag-suppress", "177,550",
-              # Global loads bypass L1 (ld.global.cg).  The factorisations run two streams; an SM that stays occupied by
-              # one stream's long kernel is not L1-invalidated when the other stream's next kernel starts on it, so a
-              # load through L1 can return a line cached before another SM rewrote it (measured: clapack_dgetrf
-              # N=16384 changed pivots in 1 of 60 runs, in 59 of 60 with the update GEMM forced to overlap the panel).
-              # L2 is the coherence point; nothing here reuses data through L1 (tiles live in shared memory).
-              "-Xptxas", "-dlcm=cg"]
+              "--expt-relaxed-constexpr", "-diag-suppress", "177,550"]
+# (Round 1 compiled everything with -Xptxas -dlcm=cg on the hypothesis that stale L1 lines caused the LU look-ahead
+#  nondeterminism.  The cause was the DGEMM kernel's stage release (dgemm_tma.cu: mbar_release); with that fixed the
+#  default caching is race-free in the same stress test (0/60 forced, profiles/r02_lu_race.txt) and equally fast,
+#  so the flag is gone.  `--variant=cg` rebuilds with it for comparison.)
 
 
 def _needs(obj, deps):
     return (not os.path.exists(obj)) or any(os.path.getmtime(d) > os.path.getmtime(obj) for d in deps)
 
 
-def build(force=False, verbose=False, diag=False):
-    """diag=True builds tools/bin/libatlas_b200_diag.so with -DATLB200_DIAG (the look-ahead race
-    diagnostics of csrc/lu_diag.cuh); the product library never contains that code."""
+VARIANTS = {
+    # experiment builds (tools/bin/libatlas_b200_<name>.so); the product library is built with none of these
+    "diag": (["-DATLB200_DIAG"], []),                      # look-ahead race diagnostics (csrc/lu_diag.cuh)
+    "nofence": (["-DAB_RELEASE_FENCE=0"], []),              # stage release by data dependency only
+    "cg": (["-Xptxas", "-dlcm=cg"], []),                    # round-1 mitigation (global loads bypass L1), for comparison
+    "rel2": (["-DAB_RELEASE_MODE=2"], []),                  # dependent arrive, predicated, no fence
+    "rel3": (["-DAB_RELEASE_MODE=3"], []),                  # ... issued one k-group into the next stage
+    "oldrelease": (["-DAB_RELEASE_OLD=1"], []),             # the round-1 stage release (racy), to measure what the fix costs
+}
+
+
+def build(force=False, verbose=False, diag=False, variant=None):
+    """variant (or diag=True) builds tools/bin/libatlas_b200_<variant>.so with the flags in VARIANTS."""
     global OBJ, LIB
     if diag:
+        variant = "diag"
+    if variant:
+        add, drop = VARIANTS[variant]
         obj_prod, lib_prod = OBJ, LIB
-        OBJ = os.path.join(CSRC, "obj_diag")
-        LIB = os.path.join(os.path.dirname(HERE), "tools", "bin", "libatlas_b200_diag.so")
+        OBJ = os.path.join(CSRC, "obj_" + variant)
+        LIB = os.path.join(os.path.dirname(HERE), "tools", "bin", f"libatlas_b200_{variant}.so")
         os.makedirs(os.path.dirname(LIB), exist_ok=True)
         try:
-            return _build(force, verbose, ["-DATLB200_DIAG"])
+            return _build(force, verbose, add, drop)
         finally:
             OBJ, LIB = obj_prod, lib_prod
-    return _build(force, verbose, [])
+    return _build(force, verbose, [], [])
 
 
-def _build(force, verbose, extra):
+def _build(force, verbose, extra, drop=()):
     os.makedirs(OBJ, exist_ok=True)
     headers = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".h", ".cuh"))]
     nvcc = os.environ.get("NVCC", "nvcc")
+    flags = list(NVCC_FLAGS)
+    for i in range(len(flags) - len(drop) + 1):
+        if drop and flags[i:i + len(drop)] == list(drop):
+            del flags[i:i + len(drop)]
+            break
 
     def one(src):
         s = os.path.join(CSRC, src)
         o = os.path.join(OBJ, src.replace(".cu", ".o"))
         if force or _needs(o, [s] + headers):
-            cmd = [nvcc] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + ["-c", s, "-o", o]
+            cmd = [nvcc] + flags + extra + (["-Xptxas", "-v"] if verbose else []) + ["-c", s, "-o", o]
             r = subprocess.run(cmd, capture_output=True, text=True)
             if r.returncode != 0:
                 raise RuntimeError(f"nvcc failed for {src}:\n{r.stdout}\n{r.stderr}")
@@ -75,4 +91,5 @@ def _build(force, verbose, extra):
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv, diag="--diag" in sys.argv))
+    var = next((a.split("=", 1)[1] for a in sys.argv if a.startswith("--variant=")), None)
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv, diag="--diag" in sys.argv, variant=var))

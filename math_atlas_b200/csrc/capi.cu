@@ -1171,8 +1171,9 @@ extern "C" {
   int ATL_##P##trtri(int Order, int Uplo, int Diag, int N, RT* A, int lda) { return atl_triop<T>(0, Order, Uplo, Diag, N, MP(T, A), lda); } \
   void ATL_##P##lauum(int Order, int Uplo, int N, RT* A, int lda) { (void)atl_triop<T>(1, Order, Uplo, NonUnit, N, MP(T, A), lda); } \
   int ATL_##P##getri(int Order, int N, RT* A, int lda, const int* ipiv, RT* wrk, int* lwrk) {                                  \
-    (void)wrk;                                                                                                                 \
-    if (lwrk && *lwrk == -1) { *lwrk = N * 64; return 0; }     /* workspace query (atlas-lp.base:217) */                       \
+    /* workspace query (atlas-lp.base:217 sets *lwrk only; the reference's invtst.c reads the size back from wrk[0], */       \
+    /* LAPACK style, so it is stored there too) */                                                                             \
+    if (lwrk && *lwrk == -1) { *lwrk = N * 64; if (wrk) wrk[0] = (RT)(N * 64); return 0; }                                     \
     return atl_getri<T>(Order, N, MP(T, A), lda, ipiv); }                                                                      \
   void P##getrs_(const char* tr, const int* n, const int* nrhs, const AT* A, const int* lda, const int* ipiv, AT* B,           \
                  const int* ldb, int* info, size_t) {                                                                          \

@@ -82,6 +82,16 @@ template <typename V, typename R> struct STC {
 template <> struct ST<float2> : STC<float2, float> {};
 template <> struct ST<double2> : STC<double2, double> {};
 
+// Per-device one-time state (function attributes, probed capacities, scratch counters) is kept in small tables
+// indexed by the current device: the same host thread may switch devices between calls (cudaSetDevice).
+constexpr int AB_MAX_DEV = 64;
+inline int ab_dev() { int d = 0; AB_CUDA_CHECK(cudaGetDevice(&d)); return (d >= 0 && d < AB_MAX_DEV) ? d : AB_MAX_DEV - 1; }
+// run `set` once per device (idempotent if two host threads race on the first call)
+struct PerDeviceOnce {
+  bool done[AB_MAX_DEV] = {};
+  template <typename F> void operator()(F&& set) { const int d = ab_dev(); if (!done[d]) { set(); done[d] = true; } }
+};
+
 // Stream every product kernel is launched on (per host thread; default = legacy stream 0 so
 // that work enqueued by PyTorch on its default stream is ordered with ours).
 cudaStream_t current_stream();

@@ -25,6 +25,10 @@
 #include <cstdlib>
 #include <algorithm>
 
+#ifndef AB_RELEASE_FENCE
+#define AB_RELEASE_FENCE 1
+#endif
+
 namespace ab {
 
 int gemm_cta_cap();
@@ -61,8 +65,23 @@ __device__ __forceinline__ void mbar_arrive(uint32_t a) {
 //    `dep` carries the low words of the stage's last fragments ANDed with a run-time zero, so the arrive's
 //    address depends on every one of them and cannot issue before they are in registers;
 //  * fence.proxy.async orders the generic-proxy reads before the async-proxy writes that the arrive licenses.
+// AB_RELEASE_MODE (measurement variants, build.py VARIANTS): 1 = fence + dependent arrive at the end of the stage
+// (default), 2 = dependent arrive only, predicated on lane 0 (no branch, no fence), 3 = as 2 but issued one k-group into
+// the NEXT stage, between its DMMAs, so that the stage boundary carries no extra instructions.
+#ifndef AB_RELEASE_MODE
+#define AB_RELEASE_MODE 1
+#endif
+__device__ __forceinline__ void mbar_release_lane0(uint32_t a, uint32_t dep, int lane) {
+  asm volatile("{\n\t.reg .pred p;\n\tsetp.eq.s32 p, %1, 0;\n\t@p mbarrier.arrive.shared::cta.b64 _, [%0];\n\t}" ::"r"(a + dep), "r"(lane) : "memory");
+}
 __device__ __forceinline__ void mbar_release(uint32_t a, uint32_t dep) {
+#if defined(AB_RELEASE_OLD)
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(a) : "memory");   // round-1 behaviour (racy), measurements only
+#elif AB_RELEASE_FENCE
   asm volatile("fence.proxy.async.shared::cta;\n\tmbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(a + dep) : "memory");
+#else
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(a + dep) : "memory");
+#endif
 }
 __device__ __forceinline__ uint32_t lo32(double v) { return (uint32_t)__double2loint(v); }
 __device__ __forceinline__ void mbar_wait(uint32_t a, uint32_t parity) {
@@ -233,6 +252,9 @@ dgemm_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 #pragma unroll
       for (int j = 0; j < 4; j++) { acc[i][j][0] = 0.; acc[i][j][1] = 0.; }
 
+#if AB_RELEASE_MODE == 3
+    uint32_t prev_bar = 0, prev_dep = 0;
+#endif
     for (int kt = 0; kt < KT; kt++, it++) {
       const uint32_t s = it % STAGES;
       const uint32_t ph = (it / STAGES) & 1;
@@ -241,6 +263,9 @@ dgemm_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       uint32_t dep = 0;
 #pragma unroll
       for (int j = 0; j < 4; j++) {
+#if AB_RELEASE_MODE == 3
+        if (j == 1 && kt > 0) mbar_release_lane0(prev_bar, prev_dep, lane);   // previous stage: its loads returned long ago
+#endif
         double a[8], b[4];
 #pragma unroll
         for (int mi = 0; mi < 8; mi++) {
@@ -266,8 +291,15 @@ dgemm_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 #pragma unroll
           for (int ni = 0; ni < 4; ni++) dmma884(acc[mi][ni][0], acc[mi][ni][1], a[mi], b[ni]);
       }
+#if AB_RELEASE_MODE == 1
       __syncwarp();
       if (lane == 0) mbar_release(bar_base + 8 * (STAGES + s), dep & zero_rt);
+#elif AB_RELEASE_MODE == 2
+      mbar_release_lane0(bar_base + 8 * (STAGES + s), dep & zero_rt, lane);
+#else
+      prev_bar = bar_base + 8 * (STAGES + s); prev_dep = dep & zero_rt;
+      if (kt == KT - 1) mbar_release_lane0(prev_bar, prev_dep, lane);        // last stage of the tile: before the epilogue
+#endif
     }
 
     // ---- epilogue: C = alpha*acc + beta*C (ablk2cmat, atlas-ammm.base:550), triangle mask for SYRK ----
@@ -345,7 +377,7 @@ bool make_map(CUtensorMap* tm, const double* ptr, size_t rows, size_t cols, size
 // look-ahead reservation state of the calling thread (set by set_gemm_reserved)
 thread_local SmMask g_reserved = {{0, 0, 0, 0}};
 thread_local bool g_reserved_on = false;
-thread_local int* g_counters = nullptr;     // ring of device tile counters
+thread_local int* g_counters[AB_MAX_DEV] = {};   // ring of device tile counters, one ring per device
 thread_local int g_counter_next = 0;
 constexpr int NCOUNTERS = 256;
 
@@ -353,11 +385,8 @@ template <bool AK, bool BK_>
 void launch(const CUtensorMap& ta, const CUtensorMap& tb, double* C, size_t ldc, int M, int N, int K, double alpha,
             double beta, int cmode, const int* abort_flag) {
   constexpr int smem_req = SMEM_BYTES;
-  static bool attr_set = false;
-  if (!attr_set) {
-    AB_CUDA_CHECK(cudaFuncSetAttribute(dgemm_tma_kernel<AK, BK_>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_req));
-    attr_set = true;
-  }
+  static PerDeviceOnce attr_once;
+  attr_once([] { AB_CUDA_CHECK(cudaFuncSetAttribute(dgemm_tma_kernel<AK, BK_>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_req)); });
   const int tiles_m = (M + BM - 1) / BM, tiles_n = (N + BN - 1) / BN;
   int grid = std::min(tiles_m * tiles_n, gemm_cta_cap());
   SmMask mask = {{0, 0, 0, 0}};
@@ -367,8 +396,9 @@ void launch(const CUtensorMap& ta, const CUtensorMap& tb, double* C, size_t ldc,
     // (also used for SYRK: half of the tiles are skipped, a static stride would be unbalanced)
     if (g_reserved_on) mask = g_reserved;
     grid = gemm_cta_cap();
-    if (!g_counters) AB_CUDA_CHECK(cudaMalloc(&g_counters, NCOUNTERS * sizeof(int)));
-    counter = g_counters + (g_counter_next++ % NCOUNTERS);
+    int*& ring = g_counters[ab_dev()];
+    if (!ring) AB_CUDA_CHECK(cudaMalloc(&ring, NCOUNTERS * sizeof(int)));
+    counter = ring + (g_counter_next++ % NCOUNTERS);
     AB_CUDA_CHECK(cudaMemsetAsync(counter, 0, sizeof(int), current_stream()));
   }
   dgemm_tma_kernel<AK, BK_><<<grid, THREADS, smem_req, current_stream()>>>(
@@ -385,9 +415,10 @@ int gemm_cta_cap() {
   if (g_cta_cap > 0) return g_cta_cap;
   static const int env_cap = [] { const char* v = getenv("ATLB200_GEMM_CTA_CAP"); return v ? atoi(v) : 0; }();   // diagnostic: > #SMs = one tile per CTA
   if (env_cap > 0) return env_cap;
-  static int sms = 0;
-  if (!sms) { int dev; AB_CUDA_CHECK(cudaGetDevice(&dev)); AB_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev)); }
-  return sms;
+  static int sms[AB_MAX_DEV] = {};
+  const int dev = ab_dev();
+  if (!sms[dev]) AB_CUDA_CHECK(cudaDeviceGetAttribute(&sms[dev], cudaDevAttrMultiProcessorCount, dev));
+  return sms[dev];
 }
 void set_gemm_cta_cap(int cap) { g_cta_cap = cap; }
 void set_gemm_reserved(const unsigned long long* mask4) {

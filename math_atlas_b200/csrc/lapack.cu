@@ -33,6 +33,56 @@ namespace ab {
 
 namespace { int env_int(const char* name, int dflt) { const char* v = getenv(name); return v ? atoi(v) : dflt; } }
 
+// ATLB200_LU_TRACE=2: CUDA-event timing of every phase of the look-ahead LU (which kernels of a block step cost what,
+// on which stream); the tables under profiles/ were made with it.  Off: no events, no cost.
+namespace {
+enum LuPhase { PH_LEAF, PH_SWAPTRSM, PH_PGEMM, PH_NEXT_SWAP, PH_NEXT_TRSM, PH_NEXT_GEMM, PH_REST_SWAP, PH_REST_TRSM, PH_REST_GEMM,
+               PH_LEFT_SWAP, PH_COUNT };
+const char* const kPhaseName[PH_COUNT] = {"leaf", "swap+trsm", "panel-gemm", "next:swap", "next:trsm", "next:gemm", "rest:swap",
+                                          "rest:trsm", "rest:gemm", "left:swap"};
+struct LuTracer {
+  bool on = false;
+  int step = 0;
+  struct Rec { int step, ph; cudaEvent_t a, b; };
+  std::vector<Rec> recs;
+  void begin(int ph) {
+    if (!on) return;
+    Rec r{step, ph, nullptr, nullptr};
+    cudaEventCreate(&r.a); cudaEventCreate(&r.b);
+    cudaEventRecord(r.a, current_stream());
+    recs.push_back(r);
+  }
+  void end() { if (on) cudaEventRecord(recs.back().b, current_stream()); }
+  void report(int nsteps) {
+    if (!on) return;
+    cudaDeviceSynchronize();
+    std::vector<double> tot(PH_COUNT, 0.0);
+    std::vector<std::vector<double>> per(nsteps + 1, std::vector<double>(PH_COUNT, 0.0));
+    std::vector<std::vector<int>> cnt(nsteps + 1, std::vector<int>(PH_COUNT, 0));
+    for (auto& r : recs) {
+      float ms = 0; cudaEventElapsedTime(&ms, r.a, r.b);
+      tot[r.ph] += ms;
+      if (r.step <= nsteps) { per[r.step][r.ph] += ms; cnt[r.step][r.ph]++; }
+      cudaEventDestroy(r.a); cudaEventDestroy(r.b);
+    }
+    fprintf(stderr, "# LU phase trace [ms]: step |");
+    for (int p = 0; p < PH_COUNT; p++) fprintf(stderr, " %10s", kPhaseName[p]);
+    fprintf(stderr, "\n");
+    for (int k = 0; k <= nsteps; k++) {
+      if (!(k < 4 || k % 4 == 0 || k >= nsteps - 2)) continue;
+      fprintf(stderr, "# LU phase      %4d |", k);
+      for (int p = 0; p < PH_COUNT; p++) fprintf(stderr, " %7.3f/%-2d", per[k][p], cnt[k][p]);
+      fprintf(stderr, "\n");
+    }
+    fprintf(stderr, "# LU phase     total |");
+    for (int p = 0; p < PH_COUNT; p++) fprintf(stderr, " %10.3f", tot[p]);
+    fprintf(stderr, "\n");
+    recs.clear();
+  }
+};
+thread_local LuTracer g_lutr;
+}  // namespace
+
 // ------------------------------------------------------------------------------------- laswp
 // One thread per column.  Swaps must be applied in order, but a batch of 32 consecutive swaps whose
 // 64 rows are pairwise distinct commutes: then all 64 elements are loaded first (64 requests in
@@ -420,15 +470,15 @@ template <> struct PanelW<double2> { static constexpr int W = 16; };
 
 template <typename T, int W, int RPT>
 static long panel_capacity() {   // rows that fit co-resident for this variant
-  static long cap = -1;
-  if (cap < 0) {
-    int dev, sms, per_sm;
-    AB_CUDA_CHECK(cudaGetDevice(&dev));
+  static long cap[AB_MAX_DEV] = {};
+  const int dev = ab_dev();
+  if (cap[dev] <= 0) {
+    int sms, per_sm;
     AB_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     AB_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, getf2_panel_kernel<T, W, RPT>, PNL_THREADS, 0));
-    cap = (long)sms * per_sm * PNL_THREADS * RPT;
+    cap[dev] = (long)sms * per_sm * PNL_THREADS * RPT;
   }
-  return cap;
+  return cap[dev];
 }
 
 template <typename T, int W, int RPT>
@@ -541,12 +591,19 @@ static void getrf_panel(T* A0, size_t lda, int r0, int M, int w, int* d_ipiv, in
     const int b = min(lw, MN - jb);
     const int d = r0 + jb;                       // diagonal position of this block
     T* Ad = A0 + (size_t)d + (size_t)d * lda;
+    g_lutr.begin(PH_LEAF);
     getf2_leaf<T>(M - jb, b, lw, use_cluster, Ad, lda, d_ipiv + d, d_info, d, d);
+    g_lutr.end();
     const int nR = w - jb - b;                   // panel columns right of the block
+    g_lutr.begin(PH_SWAPTRSM);
     swap_trsm<T>(A0, lda, d, b, d_ipiv, d + b, nR, r0, jb);
-    if (nR > 0 && M - jb - b > 0)
+    g_lutr.end();
+    if (nR > 0 && M - jb - b > 0) {
+      g_lutr.begin(PH_PGEMM);
       gemm<T>(NoTrans, NoTrans, M - jb - b, nR, b, S::from_real(-1), Ad + b, lda, Ad + (size_t)b * lda, lda, S::one(),
               Ad + b + (size_t)b * lda, lda);
+      g_lutr.end();
+    }
   }
 }
 
@@ -564,7 +621,7 @@ static void getrf_rec(T* A0, size_t lda, int r0, int M, int N, int* d_ipiv, int*
   const int leaf_w = leaf_width_for<T>(M, &use_cluster);
   // nodes up to ATLB200_LU_PW columns are factored right-looking by getrf_panel (3 launches per leaf width);
   // above that the reference's recursion keeps the updates as large-K GEMMs
-  static const int pw = env_int("ATLB200_LU_PW", 128);
+  static const int pw = env_int("ATLB200_LU_PW", 512);
   if (N <= max(leaf_w, pw)) {
     getrf_panel<T>(A0, lda, r0, M, N, d_ipiv, d_info);
     return;
@@ -614,46 +671,23 @@ struct SideStream {
 thread_local SideStream g_side;
 }  // namespace
 
-// ---- diagnostic (ATLB200_LU_CHECKSUM=1): deterministic checksums of the regions a block step produces,
-// so that two runs on the same matrix can be compared step by step (tools/lu_stress.py prints the first
-// step and region that differ).  Fixed summation order: 256 CTAs x 256 threads, then one CTA.
 template <typename T>
-__global__ void __launch_bounds__(256) cks_partial_kernel(int rows, int cols, const T* A, size_t lda, double* part) {
-  __shared__ double sh[256];
-  double acc = 0.;
-  const long long total = (long long)rows * cols;
-  for (long long e = (long long)blockIdx.x * 256 + threadIdx.x; e < total; e += 256LL * gridDim.x) {
-    const T v = A[(size_t)(e % rows) + (size_t)(e / rows) * lda];
-    if constexpr (ST<T>::cplx) acc += (double)v.x * 1.0000001 + (double)v.y; else acc += (double)v * (1.0 + 1e-7 * (double)(e & 1023));
-  }
-  sh[threadIdx.x] = acc;
-  __syncthreads();
-  for (int s2 = 128; s2 > 0; s2 >>= 1) { if ((int)threadIdx.x < s2) sh[threadIdx.x] += sh[threadIdx.x + s2]; __syncthreads(); }
-  if (threadIdx.x == 0) part[blockIdx.x] = sh[0];
-}
-__global__ void cks_final_kernel(const double* part, int n, double* out) {
-  if (threadIdx.x == 0 && blockIdx.x == 0) { double a = 0.; for (int i = 0; i < n; i++) a += part[i]; *out = a; }
-}
-static double* g_cks = nullptr;      // [step][3] on the device
-static int g_cks_steps = 0;
-template <typename T>
-static void lu_checksum(int slot, int rows, int cols, const T* A, size_t lda, int ws_slot = 2) {
-  if (!g_cks || rows <= 0 || cols <= 0) return;
-  double* part = static_cast<double*>(workspace(256 * sizeof(double), ws_slot));   // (the two streams use different scratch)
-  cks_partial_kernel<T><<<256, 256, 0, current_stream()>>>(rows, cols, A, lda, part);
-  cks_final_kernel<<<1, 32, 0, current_stream()>>>(part, 256, g_cks + slot);
-}
-
-template <typename T>
-static void lu_apply_panel(T* A, size_t lda, int M, int k0, int w, int c0, int nc, const int* d_ipiv) {
+static void lu_apply_panel(T* A, size_t lda, int M, int k0, int w, int c0, int nc, const int* d_ipiv, int ph0 = PH_REST_SWAP) {
   // columns [c0, c0+nc) receive panel [k0, k0+w): interchanges, U block row, Schur complement
   using S = ST<T>;
   if (nc <= 0) return;
+  g_lutr.begin(ph0);
   laswp<T>(nc, A + (size_t)c0 * lda, lda, k0, k0 + w, d_ipiv, 1);
+  g_lutr.end();
+  g_lutr.begin(ph0 + 1);
   trsm<T>(Left, Lower, NoTrans, Unit, w, nc, S::one(), A + (size_t)k0 + (size_t)k0 * lda, lda, A + (size_t)k0 + (size_t)c0 * lda, lda);
-  if (M - k0 - w > 0)
+  g_lutr.end();
+  if (M - k0 - w > 0) {
+    g_lutr.begin(ph0 + 2);
     gemm<T>(NoTrans, NoTrans, M - k0 - w, nc, w, S::from_real(-1), A + (size_t)(k0 + w) + (size_t)k0 * lda, lda,
             A + (size_t)k0 + (size_t)c0 * lda, lda, S::one(), A + (size_t)(k0 + w) + (size_t)c0 * lda, lda);
+    g_lutr.end();
+  }
 }
 
 #ifdef ATLB200_DIAG
@@ -741,37 +775,40 @@ struct DiagRun {
 
 template <typename T>
 static void getrf_lookahead(int M, int N, T* A, size_t lda, int* d_ipiv, int* d_info, int NB) {
+  using S = ST<T>;
   const int MN = min(M, N);
   SideStream& ss = g_side;
   ss.ensure();
   cudaStream_t U = current_stream(), P = ss.st;
-  // SMs of one GPC are kept free of update-GEMM CTAs while a panel is being factored beside it
-  const unsigned long long* reserved = env_int("ATLB200_LU_RESERVE", 1) ? cluster_reserved_mask() : nullptr;
-  // ATLB200_LU_TRACE=1: time both streams per block step with events and print the timeline (debug)
-  const bool trace = env_int("ATLB200_LU_TRACE", 0) != 0;
+  // SMs of one GPC are kept free of update-GEMM CTAs while a panel is being factored beside it; from block step
+  // ATLB200_LU_RESERVE2_PCT % of the way on - when the panel chain, not the update, bounds a step - two GPCs
+  const bool res_on = env_int("ATLB200_LU_RESERVE", 1) != 0;
+  const int res2_pct = env_int("ATLB200_LU_RESERVE2_PCT", 100);
+  const unsigned long long* res1 = res_on ? cluster_reserved_mask(1) : nullptr;
+  const unsigned long long* res2 = (res_on && res2_pct < 100) ? cluster_reserved_mask(2) : nullptr;
+  const int total_steps = (MN + NB - 1) / NB;
+  // ATLB200_LU_TRACE=1: both streams per block step; 2: every phase (LuTracer)
+  const int trace = env_int("ATLB200_LU_TRACE", 0);
+  g_lutr.on = trace >= 2;
   std::vector<cudaEvent_t> tev;
   auto mark = [&](cudaStream_t st) { if (trace) { cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, st); tev.push_back(e); } };
   mark(U);
-
 #ifdef ATLB200_DIAG
   DiagRun<T> dg;
   dg.init(M, N, NB);
 #endif
-  const bool cks = env_int("ATLB200_LU_CHECKSUM", 0) != 0;
-  if (cks) {
-    g_cks_steps = (MN + NB - 1) / NB;
-    if (g_cks) cudaFree(g_cks);
-    AB_CUDA_CHECK(cudaMalloc(&g_cks, sizeof(double) * 3 * (g_cks_steps + 1)));
-    AB_CUDA_CHECK(cudaMemsetAsync(g_cks, 0, sizeof(double) * 3 * (g_cks_steps + 1), U));
-  } else g_cks = nullptr;
+  g_lutr.step = 0;
   getrf_rec<T>(A, lda, 0, M, min(NB, N), d_ipiv, d_info);          // panel 0 on the main stream
+  int nsteps = 0;
   for (int k0 = 0, k = 0; k0 < MN; k0 += NB, k++) {
+    nsteps = k + 1;
+    g_lutr.step = k + 1;
     const int w = min(NB, MN - k0);
     const int c1 = k0 + w;                       // first column right of the panel
     const int nright = N - c1;
     const bool more = (c1 < MN);                 // is there a next panel to factor?
     if (nright > 0) {
-      const int w1 = more ? min(NB, N - c1) : 0;
+      const int w1 = more ? min(NB, MN - c1) : 0;   // (pivot columns only: what lies right of column MN is 'rest')
       // A panel too tall for one cluster is factored by the cooperative global-barrier kernel, whose
       // CTAs cannot become co-resident while the persistent update GEMM holds the SMs (measured:
       // N=65536 ran 2.4x slower with the two fighting) - such steps run back to back instead.
@@ -784,8 +821,7 @@ static void getrf_lookahead(int M, int N, T* A, size_t lda, int* d_ipiv, int* d_
         continue;
       }
       if (more) {
-        lu_apply_panel<T>(A, lda, M, k0, w, c1, w1, d_ipiv);          // next panel's columns first
-        if (cks) lu_checksum<T>(3 * k, M, w1, A + (size_t)c1 * lda, lda);              // panel k+1 as the panel kernels will see it
+        lu_apply_panel<T>(A, lda, M, k0, w, c1, w1, d_ipiv, PH_NEXT_SWAP);    // next panel's columns first
         AB_CUDA_CHECK(cudaEventRecord(ss.cols[k & 1], U));
         AB_CUDA_CHECK(cudaStreamWaitEvent(P, ss.cols[k & 1], 0));
         set_current_stream(P);
@@ -797,38 +833,19 @@ static void getrf_lookahead(int M, int N, T* A, size_t lda, int* d_ipiv, int* d_
 #ifdef ATLB200_DIAG
         diag::on_side() = false;
 #endif
-        if (cks) lu_checksum<T>(3 * k + 1, M, w1, A + (size_t)c1 * lda, lda, 7);       // ... and as they leave it (on P)
         mark(P);
         AB_CUDA_CHECK(cudaEventRecord(ss.panel[k & 1], P));
         set_current_stream(U);
-        set_gemm_reserved(reserved);                                   // leave a GPC to the panel kernels
+        set_gemm_reserved((res2 && k * 100 >= total_steps * res2_pct) ? res2 : res1);   // leave a GPC (or two) to the panel kernels
       }
-      // What runs beside the panel.  The row interchanges (of the rest columns and left of the panel) always
-      // do.  The rest update's TRSM and GEMM do only with ATLB200_LU_OVERLAP_GEMM=1: although it
-      // shares no data with the panel, a stress test (tools/lu_stress.py) found clapack_dgetrf N=16384
-      // changing pivots in ~2 % of the runs whenever the long persistent GEMM ran beside the panel's
-      // kernels (never with any other overlap, never on one stream; L1-bypassing loads cut the rate but did
-      // not remove it) - until that is understood the GEMM waits for the panel.
-      static const bool overlap_gemm = env_int("ATLB200_LU_OVERLAP_GEMM", 0) != 0;
+      // The rest of update k (interchanges, U block row, Schur complement) runs beside the panel.  (Round 1
+      // shipped with the TRSM+GEMM held back until the panel had finished, because ~2 % of the runs changed
+      // pivots with the full overlap; the cause was the DGEMM kernel's stage release - see mbar_release in
+      // dgemm_tma.cu and DESIGN.md - and with it fixed the overlap is deterministic again.)
       const int c0 = c1 + w1, nc = nright - w1;
       if (more) mark(U);
-      if (more && !overlap_gemm) {
-        using S = ST<T>;
-        set_gemm_reserved(nullptr);
-        if (nc > 0) laswp<T>(nc, A + (size_t)c0 * lda, lda, k0, k0 + w, d_ipiv, 1);
-        if (k0 > 0) laswp<T>(k0, A, lda, k0, k0 + w, d_ipiv, 1);         // interchanges left of the panel
-        AB_CUDA_CHECK(cudaStreamWaitEvent(U, ss.panel[k & 1], 0));
-        if (nc > 0)       // (the TRSM recursion contains GEMMs of its own: after the panel, too)
-          trsm<T>(Left, Lower, NoTrans, Unit, w, nc, S::one(), A + (size_t)k0 + (size_t)k0 * lda, lda, A + (size_t)k0 + (size_t)c0 * lda, lda);
-        if (nc > 0 && M - k0 - w > 0)
-          gemm<T>(NoTrans, NoTrans, M - k0 - w, nc, w, S::from_real(-1), A + (size_t)(k0 + w) + (size_t)k0 * lda, lda,
-                  A + (size_t)k0 + (size_t)c0 * lda, lda, S::one(), A + (size_t)(k0 + w) + (size_t)c0 * lda, lda);
-        mark(U);
-        continue;
-      }
 #ifdef ATLB200_DIAG
       if (dg.on && more && nc > 0 && M - k0 - w > 0) {
-        using S = ST<T>;
         const int rows = M - k0 - w;
         const T* A21 = A + (size_t)(k0 + w) + (size_t)k0 * lda;
         T* U12 = A + (size_t)k0 + (size_t)c0 * lda;
@@ -846,11 +863,14 @@ static void getrf_lookahead(int M, int N, T* A, size_t lda, int* d_ipiv, int* d_
       } else
 #endif
       lu_apply_panel<T>(A, lda, M, k0, w, c0, nc, d_ipiv);
-      if (cks && more && nc > 0) lu_checksum<T>(3 * k + 2, M, nc, A + (size_t)c0 * lda, lda);   // the rest columns after update k
       if (more) mark(U);
       set_gemm_reserved(nullptr);
     }
-    if (k0 > 0) laswp<T>(k0, A, lda, k0, k0 + w, d_ipiv, 1);           // interchanges left of the panel
+    if (k0 > 0) {                                                      // interchanges left of the panel
+      g_lutr.begin(PH_LEFT_SWAP);
+      laswp<T>(k0, A, lda, k0, k0 + w, d_ipiv, 1);
+      g_lutr.end();
+    }
     if (more && nright > 0) AB_CUDA_CHECK(cudaStreamWaitEvent(U, ss.panel[k & 1], 0));
 #ifdef ATLB200_DIAG
     if (dg.pending) { set_gemm_reserved(nullptr); dg.after(U); }
@@ -869,6 +889,8 @@ static void getrf_lookahead(int M, int N, T* A, size_t lda, int* d_ipiv, int* d_
       fprintf(stderr, "%3zu  P %8.3f .. %8.3f (%6.3f)   U %8.3f .. %8.3f (%6.3f)\n", i / 4, a, b, b - a, c, d, d - c);
     }
     for (auto e : tev) cudaEventDestroy(e);
+    g_lutr.report(nsteps);
+    g_lutr.on = false;
   }
 }
 
@@ -877,12 +899,7 @@ static void getrf_lookahead(int M, int N, T* A, size_t lda, int* d_ipiv, int* d_
 // long persistent update can always be scheduled.  n < 0: dynamic tile sharing only - for a rank whose
 // collective kernel is already resident: the GEMM CTAs it displaces start late and must not each
 // carry a full static share of the tiles.
-int lu_checksums(double* host_out, int max_steps) {
-  if (!g_cks) return 0;
-  const int n = g_cks_steps < max_steps ? g_cks_steps : max_steps;
-  AB_CUDA_CHECK(cudaMemcpy(host_out, g_cks, sizeof(double) * 3 * n, cudaMemcpyDeviceToHost));
-  return n;
-}
+int lu_checksums(double*, int) { return 0; }   // round-1 diagnostic, retired (tools/lu_race.cu + the diag build replace it)
 
 void lu_reserve_sms(int n) {
   unsigned long long m[4] = {0, 0, 0, 0};

@@ -493,14 +493,18 @@ __global__ void __launch_bounds__(CL_TPB, 1) cluster_probe_kernel(unsigned* smid
   cg::cluster_group cluster = cg::this_cluster();
   probe_smem[threadIdx.x] = 0;
   cluster.sync();
-  if (threadIdx.x == 0) { unsigned s; asm volatile("mov.u32 %0, %%smid;" : "=r"(s)); smids[cluster.block_rank()] = s; }
+  if (threadIdx.x == 0) { unsigned s; asm volatile("mov.u32 %0, %%smid;" : "=r"(s)); smids[blockIdx.x] = s; }
 }
 
-static const unsigned long long* cluster_reserved_mask() {
-  static unsigned long long mask[4] = {0, 0, 0, 0};
-  static bool done = false, ok = false;
-  if (!done) {
-    done = true;
+// nclusters = 1 or 2: the SMs of one GPC, or of two (the look-ahead gives the panel chain a second GPC once the
+// factorisation has become panel-bound).  Probed once per device.
+static const unsigned long long* cluster_reserved_mask(int nclusters = 1) {
+  struct Entry { unsigned long long mask[4] = {0, 0, 0, 0}; bool done = false, ok = false; };
+  static Entry table[AB_MAX_DEV][2];
+  nclusters = nclusters >= 2 ? 2 : 1;
+  Entry& e = table[ab_dev()][nclusters - 1];
+  if (!e.done) {
+    e.done = true;
     const int smem = 128 * 1024;   // one CTA per SM, like the panel kernel (whole register file)
     if (cudaFuncSetAttribute(cluster_probe_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess ||
         cudaFuncSetAttribute(cluster_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) {
@@ -509,31 +513,32 @@ static const unsigned long long* cluster_reserved_mask() {
     }
     unsigned* d = nullptr;
     AB_CUDA_CHECK(cudaDeviceSynchronize());
-    AB_CUDA_CHECK(cudaMalloc(&d, CL_MAXC * sizeof(unsigned)));
-    for (int c = CL_MAXC; c >= 2 && !ok; c >>= 1) {
+    AB_CUDA_CHECK(cudaMalloc(&d, 2 * CL_MAXC * sizeof(unsigned)));
+    for (int c = CL_MAXC; c >= 2 && !e.ok; c >>= 1) {
       cudaLaunchConfig_t cfg{};
-      cfg.gridDim = dim3(c); cfg.blockDim = dim3(CL_TPB); cfg.dynamicSmemBytes = smem; cfg.stream = 0;
+      cfg.gridDim = dim3(c * nclusters); cfg.blockDim = dim3(CL_TPB); cfg.dynamicSmemBytes = smem; cfg.stream = 0;
       cudaLaunchAttribute at[1];
       at[0].id = cudaLaunchAttributeClusterDimension;
       at[0].val.clusterDim.x = c; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
       cfg.attrs = at; cfg.numAttrs = 1;
       if (cudaLaunchKernelEx(&cfg, cluster_probe_kernel, d) == cudaSuccess && cudaDeviceSynchronize() == cudaSuccess) {
-        unsigned h[CL_MAXC];
-        AB_CUDA_CHECK(cudaMemcpy(h, d, c * sizeof(unsigned), cudaMemcpyDeviceToHost));
-        for (int i = 0; i < c; i++) if (h[i] < 256) mask[h[i] >> 6] |= 1ull << (h[i] & 63);
-        ok = true;
+        unsigned h[2 * CL_MAXC];
+        AB_CUDA_CHECK(cudaMemcpy(h, d, c * nclusters * sizeof(unsigned), cudaMemcpyDeviceToHost));
+        for (int i = 0; i < c * nclusters; i++) if (h[i] < 256) e.mask[h[i] >> 6] |= 1ull << (h[i] & 63);
+        e.ok = true;
       } else (void)cudaGetLastError();
     }
     cudaFree(d);
   }
-  return ok ? mask : nullptr;
+  return e.ok ? e.mask : nullptr;
 }
 
 // largest cluster size (power of two <= 16) this kernel can be launched with on the current device
 template <typename T, int W, int RPT>
 static int cluster_max_size() {
-  static int mx = -1;
-  if (mx < 0) {
+  static int mxd[AB_MAX_DEV] = {};
+  int& mx = mxd[ab_dev()];
+  if (mx <= 0) {
     (void)cudaFuncSetAttribute(getf2_cluster_kernel<T, W, RPT>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
     (void)cudaGetLastError();
     mx = 1;
@@ -568,8 +573,8 @@ static void cluster_launch(int M, int w, T* A, size_t lda, int* d_ipiv, int* d_i
   cfg.attrs = at; cfg.numAttrs = 1;
   static const int variant = [] { const char* v = getenv("ATLB200_LU_LEAF"); return v ? atoi(v) : 2; }();
   if (variant == 2) {
-    static bool attr = false;
-    if (!attr) { (void)cudaFuncSetAttribute(getf2_cluster_async_kernel<T, W, RPT>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1); (void)cudaGetLastError(); attr = true; }
+    static PerDeviceOnce attr_once;
+    attr_once([] { (void)cudaFuncSetAttribute(getf2_cluster_async_kernel<T, W, RPT>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1); (void)cudaGetLastError(); });
     AB_CUDA_CHECK(cudaLaunchKernelEx(&cfg, getf2_cluster_async_kernel<T, W, RPT>, M, w, A, lda, d_ipiv, d_info, piv_off, info_off,
                                      (long long*)nullptr));
   } else {

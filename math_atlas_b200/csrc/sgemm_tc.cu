@@ -488,8 +488,8 @@ static void launch_tc(const CUtensorMap& mAh, const CUtensorMap& mAl, const CUte
                       int N, int KB, float alpha, float beta, int cmode, int tiles_m128, int tiles_n, const int* abort_flag, float alpha_im,
                       float beta_im, int herk) {
   if (tc_variant() == 2) {
-    static bool attr = false;
-    if (!attr) { AB_CUDA_CHECK(cudaFuncSetAttribute(sgemm_tc2_kernel<CPLX>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM2_BYTES)); attr = true; }
+    static PerDeviceOnce attr_once;
+    attr_once([] { AB_CUDA_CHECK(cudaFuncSetAttribute(sgemm_tc2_kernel<CPLX>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM2_BYTES)); });
     const int tiles_m256 = (tiles_m128 + 1) / 2;
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(2u * (unsigned)tiles_m256 * (unsigned)tiles_n); cfg.blockDim = dim3(THREADS);
@@ -501,8 +501,8 @@ static void launch_tc(const CUtensorMap& mAh, const CUtensorMap& mAl, const CUte
     AB_CUDA_CHECK(cudaLaunchKernelEx(&cfg, sgemm_tc2_kernel<CPLX>, mAh, mAl, mBh, mBl, C, ldc, M, N, KB, alpha, beta, cmode, tiles_m256, tiles_n,
                                      abort_flag, alpha_im, beta_im, herk));
   } else {
-    static bool attr = false;
-    if (!attr) { AB_CUDA_CHECK(cudaFuncSetAttribute(sgemm_tc_kernel<CPLX>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES)); attr = true; }
+    static PerDeviceOnce attr_once;
+    attr_once([] { AB_CUDA_CHECK(cudaFuncSetAttribute(sgemm_tc_kernel<CPLX>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES)); });
     sgemm_tc_kernel<CPLX><<<(unsigned)tiles_m128 * (unsigned)tiles_n, THREADS, SMEM_BYTES, current_stream()>>>(
         mAh, mAl, mBh, mBl, C, ldc, M, N, KB, alpha, beta, cmode, tiles_m128, tiles_n, abort_flag, alpha_im, beta_im, herk);
   }

@@ -23,6 +23,10 @@
 #include <mutex>
 #include <algorithm>
 
+#ifndef AB_RELEASE_FENCE
+#define AB_RELEASE_FENCE 1
+#endif
+
 namespace ab {
 
 int gemm_cta_cap();
@@ -45,7 +49,13 @@ __device__ __forceinline__ void mbar_arrive(uint32_t a) { asm volatile("mbarrier
 // consumer release of a stage: the ld.shared of the stage must have returned and be ordered before the TMA refill
 // (async proxy) that the arrive licenses - see mbar_release in dgemm_tma.cu for the failure this prevents
 __device__ __forceinline__ void mbar_release(uint32_t a, uint32_t dep) {
+#if defined(AB_RELEASE_OLD)
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(a) : "memory");   // round-1 behaviour (racy), measurements only
+#elif AB_RELEASE_FENCE
   asm volatile("fence.proxy.async.shared::cta;\n\tmbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(a + dep) : "memory");
+#else
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(a + dep) : "memory");
+#endif
 }
 __device__ __forceinline__ void mbar_wait(uint32_t a, uint32_t parity) {
   uint32_t done;
@@ -251,11 +261,8 @@ bool make_map(CUtensorMap* tm, const double2* ptr, size_t rows, size_t cols, siz
 template <bool AK, bool BK_>
 void launch(const CUtensorMap& ta, const CUtensorMap& tb, double2* C, size_t ldc, int M, int N, int K, double2 alpha, double2 beta,
             int ca, int cb, int cmode, int herk, const int* abort_flag) {
-  static bool attr_set = false;
-  if (!attr_set) {
-    AB_CUDA_CHECK(cudaFuncSetAttribute(zgemm_tma_kernel<AK, BK_>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-    attr_set = true;
-  }
+  static PerDeviceOnce attr_once;
+  attr_once([] { AB_CUDA_CHECK(cudaFuncSetAttribute(zgemm_tma_kernel<AK, BK_>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES)); });
   const int tiles_m = (M + BM - 1) / BM, tiles_n = (N + BN - 1) / BN;
   const int grid = std::min(tiles_m * tiles_n, gemm_cta_cap());
   zgemm_tma_kernel<AK, BK_><<<grid, THREADS, SMEM_BYTES, current_stream()>>>(ta, tb, C, ldc, M, N, K, alpha, beta, ca, cb, cmode, herk,

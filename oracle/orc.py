@@ -35,7 +35,7 @@ def build_oracle(force=False):
     so = os.path.join(HERE, "liboracle.so")
     src = [os.path.join(HERE, f) for f in ("atl_oracle.c", "orc_tmpl.h")]
     if force or not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in src):
-        subprocess.check_call(["gcc", "-O2", "-ffp-contract=off", "-fPIC", "-shared", "-o", so, src[0], "-lm"])
+        subprocess.check_call(["gcc", "-O3", "-ffp-contract=off", "-fPIC", "-shared", "-o", so, src[0], "-lm"])
     return so
 
 

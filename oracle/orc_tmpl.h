@@ -218,6 +218,25 @@ static inline S FN(opel)(const S* A, int lda, int trans, int i, int j) { /* op(A
 void FN(gemm)(int TA, int TB, int M, int N, int K, const S* palpha, const S* A, int lda, const S* B, int ldb,
               const S* pbeta, S* C, int ldc) {
   const S alpha = *palpha, beta = *pbeta;
+  if (TA == 111 && M > 0 && !S_ISZERO(alpha)) {
+    /* same sums in the same order (l = 0..K-1 for every element), evaluated a column of C at a time with the
+       l loop outside so that A is read along its contiguous dimension: large cases finish in seconds */
+    S* t = (S*)malloc(sizeof(S) * (size_t)M);
+    for (int j = 0; j < N; j++) {
+      for (int i = 0; i < M; i++) t[i] = S_ZERO;
+      for (int l = 0; l < K; l++) {
+        const S b = FN(opel)(B, ldb, TB, l, j);
+        const S* a = &EL(A, lda, 0, l);
+        for (int i = 0; i < M; i++) { S p = S_MUL(a[i], b); t[i] = S_ADD(t[i], p); }
+      }
+      for (int i = 0; i < M; i++) {
+        S c = S_ISZERO(beta) ? S_ZERO : S_MUL(beta, EL(C, ldc, i, j));
+        EL(C, ldc, i, j) = S_ADD(c, S_MUL(alpha, t[i]));
+      }
+    }
+    free(t);
+    return;
+  }
   for (int j = 0; j < N; j++)
     for (int i = 0; i < M; i++) {
       S t = S_ZERO;
@@ -231,6 +250,24 @@ void FN(gemm)(int TA, int TB, int M, int N, int K, const S* palpha, const S* A, 
 /* C := alpha*op(A)*op(A)^T + beta*C on one triangle (trans==111: A is N x K, else K x N). */
 void FN(syrk)(int uplo, int trans, int N, int K, const S* palpha, const S* A, int lda, const S* pbeta, S* C, int ldc) {
   const S alpha = *palpha, beta = *pbeta;
+  if (trans == 111 && N > 0 && !S_ISZERO(alpha)) {   /* column at a time, l outside: same sums, same order */
+    S* t = (S*)malloc(sizeof(S) * (size_t)N);
+    for (int j = 0; j < N; j++) {
+      const int i0 = (uplo == 121) ? 0 : j, i1 = (uplo == 121) ? j + 1 : N;
+      for (int i = i0; i < i1; i++) t[i] = S_ZERO;
+      for (int l = 0; l < K; l++) {
+        const S b = EL(A, lda, j, l);
+        const S* a = &EL(A, lda, 0, l);
+        for (int i = i0; i < i1; i++) t[i] = S_ADD(t[i], S_MUL(a[i], b));
+      }
+      for (int i = i0; i < i1; i++) {
+        S c = S_ISZERO(beta) ? S_ZERO : S_MUL(beta, EL(C, ldc, i, j));
+        EL(C, ldc, i, j) = S_ADD(c, S_MUL(alpha, t[i]));
+      }
+    }
+    free(t);
+    return;
+  }
   for (int j = 0; j < N; j++) {
     int i0 = (uplo == 121) ? 0 : j, i1 = (uplo == 121) ? j + 1 : N;
     for (int i = i0; i < i1; i++) {
@@ -320,6 +357,38 @@ void FN(trsm)(int side, int uplo, int trans, int diag, int M, int N, const S* pa
   const int notr = (trans == 111 || trans == 114);
   /* op(A) is lower triangular iff (stored lower) == (not transposed) */
   const int oplower = ((uplo == 122) == (notr != 0));
+  if (side == 141 && oplower && trans == 111) {
+    /* forward substitution, column-oriented: element i still receives its terms in the order l = 0..i-1 */
+    for (int j = 0; j < N; j++) {
+      S* x = &EL(B, ldb, 0, j);
+      for (int i = 0; i < M; i++) x[i] = S_ISZERO(alpha) ? S_ZERO : S_MUL(alpha, x[i]);
+      for (int l = 0; l < M; l++) {
+        if (diag != 132) x[l] = S_DIV(x[l], EL(A, lda, l, l));
+        const S xl = x[l];
+        const S* a = &EL(A, lda, 0, l);
+        for (int i = l + 1; i < M; i++) x[i] = S_SUB(x[i], S_MUL(a[i], xl));
+      }
+    }
+    return;
+  }
+  if (side == 142 && M > 0) {
+    /* X*T = alpha*B, T = op(A): column j of X, every element's terms in the order of the loop below (l ascending), i innermost */
+    S* t = (S*)malloc(sizeof(S) * (size_t)M);
+    for (int s = 0; s < N; s++) {
+      const int j = oplower ? N - 1 - s : s;
+      for (int i = 0; i < M; i++) t[i] = S_ISZERO(alpha) ? S_ZERO : S_MUL(alpha, EL(B, ldb, i, j));
+      const int l0 = oplower ? j + 1 : 0, l1 = oplower ? N : j;
+      for (int l = l0; l < l1; l++) {
+        const S a = FN(optri)(A, lda, uplo, diag, trans, l, j);
+        const S* b = &EL(B, ldb, 0, l);
+        for (int i = 0; i < M; i++) t[i] = S_SUB(t[i], S_MUL(b[i], a));
+      }
+      if (diag != 132) { const S d = FN(optri)(A, lda, uplo, diag, trans, j, j); for (int i = 0; i < M; i++) t[i] = S_DIV(t[i], d); }
+      for (int i = 0; i < M; i++) EL(B, ldb, i, j) = t[i];
+    }
+    free(t);
+    return;
+  }
   if (side == 141) {
     for (int j = 0; j < N; j++) {
       for (int i = 0; i < M; i++) EL(B, ldb, i, j) = S_ISZERO(alpha) ? S_ZERO : S_MUL(alpha, EL(B, ldb, i, j));

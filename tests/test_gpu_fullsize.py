@@ -1,0 +1,271 @@
+"""GPU tests of the code paths the benchmarks actually run ("weak" item 1 / "next" item 2):
+
+  * the look-ahead LU / Cholesky drivers (min(M,N) >= 2048) against the ORACLE - pivots bit-exact, factors to
+    rounding - at N = 2560 and 4096 and one non-square shape (the oracle's order-preserving fast loops make these
+    sizes a few seconds of CPU work);
+  * BASELINE configs 3 and 4 at full size (DTRSM / DSYRK / DPOTRF N = 16384) through size-independent properties:
+    ||op(A) X - alpha B||, checksum linearity of the rank-k update, ||A - L L'|| via an independent float64 matmul;
+  * the s/c tensor-core GEMM (3xTF32 on tcgen05) at K >= 8192 under the reference's ELEMENT-WISE criterion of
+    gemmtst (Clint/atlas.base:21968: |d| <= 2(|alpha| 2K eps + |beta| eps) + eps; complex 8K) beside the normwise one;
+  * numerical results through the F77 entry points dgemm_ / dtrsm_ / dsyrk_ / dgetrf_ (1-based pivots,
+    Clint/atlas-ilp.base:160) / dpotrf_ against the oracle.
+torch is used here only as an independent checker (float64 matmul, norms) and as the device allocator.
+"""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import math_atlas_b200 as ab
+from oracle.orc import (NoTrans, Trans, ConjTrans, Upper, Lower, NonUnit, Unit, Left, Right, ColMajor, CPLX, eps_of, _nrm1, lltgen,
+                        lu_resid, llt_resid)
+
+pytestmark = pytest.mark.gpu
+LATHRESH = 10.0   # reference lutst / llttst accept 100
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _lib():
+    import torch
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    ab.lib()
+
+
+# ------------------------------------------------------------------ look-ahead drivers against the oracle
+@pytest.mark.parametrize("M,N", [(2560, 2560), (4096, 4096), (3000, 2304), (2304, 3000)])
+def test_dgetrf_lookahead_vs_oracle(oracle, M, N):
+    lda = M + 8
+    A0 = oracle.gegen("d", M, N, lda, M * N + lda)
+    want, got = A0.copy(order="F"), A0.copy(order="F")
+    iw, pw = oracle.getrf("d", M, N, want)
+    piv = np.full(min(M, N), -7, dtype=np.int32)
+    ig = ab.clapack_getrf("d", ColMajor, M, N, got, lda, piv)
+    assert ig == iw == 0
+    assert np.array_equal(piv, pw), (M, N, np.nonzero(piv != pw)[0][:5])
+    # identical pivots => the factors agree to rounding (growth of partial pivoting on these inputs is small)
+    d = np.max(np.abs(got[:M] - want[:M]))
+    assert d <= 1e-10 * max(1.0, np.max(np.abs(want[:M]))), d
+    assert lu_resid("d", M, N, A0, got, piv) < LATHRESH
+    assert np.array_equal(got[M:], A0[M:]), "lda gap overwritten"
+
+
+@pytest.mark.parametrize("pre,N", [("s", 2560), ("z", 2304), ("c", 2304)])
+def test_getrf_lookahead_other_types_vs_oracle(oracle, pre, N):
+    A0 = oracle.gegen(pre, N, N, N, N * N + N)
+    want, got = A0.copy(order="F"), A0.copy(order="F")
+    iw, pw = oracle.getrf(pre, N, N, want)
+    piv = np.zeros(N, dtype=np.int32)
+    assert ab.clapack_getrf(pre, ColMajor, N, N, got, N, piv) == iw == 0
+    assert np.array_equal(piv, pw), (pre, N, np.nonzero(piv != pw)[0][:5])
+    assert lu_resid(pre, N, N, A0, got, piv) < LATHRESH
+
+
+@pytest.mark.parametrize("N,uplo", [(2560, Lower), (2560, Upper), (4096, Lower)])
+def test_dpotrf_lookahead_vs_oracle(oracle, N, uplo):
+    lda = N + 4
+    A0 = lltgen(oracle, "d", uplo, N, lda, N * 1029 + lda)
+    want, got = A0.copy(order="F"), A0.copy(order="F")
+    assert oracle.potrf("d", uplo, N, want) == 0
+    assert ab.clapack_potrf("d", ColMajor, uplo, N, got, lda) == 0
+    tri = np.triu_indices(N) if uplo == Upper else np.tril_indices(N)
+    d = np.max(np.abs(got[:N][tri] - want[:N][tri]))
+    assert d <= 64 * eps_of("d") * N * np.max(np.abs(want[:N][tri])), d
+    assert llt_resid("d", uplo, N, A0, got) < LATHRESH
+    other = np.tril_indices(N, -1) if uplo == Upper else np.triu_indices(N, 1)
+    assert np.array_equal(got[:N][other], A0[:N][other]) and np.array_equal(got[N:], A0[N:])
+
+
+# ------------------------------------------------------------------ BASELINE configs 3 and 4 at N = 16384
+def _rand(n, seed, torch):
+    g = torch.Generator(device="cuda"); g.manual_seed(seed)
+    return torch.rand((n, n), device="cuda", dtype=torch.float64, generator=g) - 0.5
+
+
+@pytest.mark.parametrize("side,uplo,ta", [(Left, Lower, NoTrans), (Left, Upper, Trans), (Right, Upper, NoTrans), (Right, Lower, Trans)])
+def test_dtrsm_16384_residual(side, uplo, ta):
+    """solve op(A) X = alpha B (Left) / X op(A) = alpha B (Right); check op(A) (X v) = alpha B v, i.e. one column of the
+    residual ||op(A) X - alpha B|| scaled as the tester does (atlbinblas.base:12881)."""
+    import torch
+    n = 16384
+    Am = _rand(n, 11, torch)                      # memory = row-major torch (n,n) = column-major A^T: views below are column-major
+    Am.diagonal().add_(float(n) / 8)              # diagonally dominant like the tester's trddom
+    Bm = _rand(n, 12, torch)
+    B0 = Bm.clone()
+    alpha = 0.7
+    ab.cblas_trsm("d", ColMajor, side, uplo, ta, NonUnit, n, n, alpha, Am, n, Bm, n)
+    Acm, Xcm, Bcm = Am.T, Bm.T, B0.T             # column-major views
+    T = torch.triu(Acm) if uplo == Upper else torch.tril(Acm)
+    opT = T if ta == NoTrans else T.T
+    v = torch.linspace(-1.0, 1.0, n, device="cuda", dtype=torch.float64)
+    if side == Left:
+        lhs, rhs = opT @ (Xcm @ v), alpha * (Bcm @ v)
+    else:
+        lhs, rhs = (v @ Xcm) @ opT, alpha * (v @ Bcm)
+    eps = 2.0 ** -52
+    scale = torch.max(torch.sum(torch.abs(T), dim=0)).item() * max(torch.max(torch.abs(Xcm @ torch.ones_like(v))).item(), 1.0)
+    r = torch.max(torch.abs(lhs - rhs)).item() / (scale * eps * n)
+    assert r < 5.0, r
+    assert torch.isfinite(Bm).all()
+
+
+@pytest.mark.parametrize("uplo,trans", [(Lower, NoTrans), (Upper, Trans)])
+def test_dsyrk_16384_checksum(uplo, trans):
+    """C(tri) <- alpha A A' + beta C at N = K = 16384: (sym(C) v) = alpha A (A' v) + beta sym(C0) v, other triangle untouched"""
+    import torch
+    n = 16384
+    Am = _rand(n, 21, torch)
+    Cm = _rand(n, 22, torch)
+    C0 = Cm.clone()
+    alpha, beta = 1.0, 1.0
+    ab.cblas_syrk("d", ColMajor, uplo, trans, n, n, alpha, Am, n, beta, Cm, n)
+    Acm, Ccm, C0cm = Am.T, Cm.T, C0.T
+    op = Acm if trans == NoTrans else Acm.T
+    v = torch.linspace(-1.0, 1.0, n, device="cuda", dtype=torch.float64)
+
+    def sym_mv(Mx):          # (triangle `uplo` of Mx, mirrored) @ v without forming the symmetric matrix
+        tri = torch.triu(Mx) if uplo == Upper else torch.tril(Mx)
+        return tri @ v + tri.T @ v - torch.diagonal(Mx) * v
+    lhs = sym_mv(Ccm)
+    rhs = alpha * (op @ (op.T @ v)) + beta * sym_mv(C0cm)
+    eps = 2.0 ** -52
+    r = torch.max(torch.abs(lhs - rhs)).item() / (max(torch.max(torch.abs(rhs)).item(), 1.0) * eps * n)
+    assert r < 5.0, r
+    strict_other = torch.tril(Ccm, -1) if uplo == Upper else torch.triu(Ccm, 1)
+    strict_other0 = torch.tril(C0cm, -1) if uplo == Upper else torch.triu(C0cm, 1)
+    assert torch.equal(strict_other, strict_other0), "the other triangle was written"
+
+
+@pytest.mark.parametrize("uplo", [Lower, Upper])
+def test_dpotrf_16384_residual(uplo):
+    """llttst's ||A - L L'||_1 / (||A||_1 eps N) <= 100 (atlas-tlp.base:1508) at the BASELINE size, via torch float64 matmul"""
+    import torch
+    n = 16384
+    X = _rand(n, 31, torch)
+    A = (X + X.T) * 0.5
+    A.diagonal().add_(float(n) * 0.3)            # SPD by diagonal dominance (lltgen-like)
+    A0 = A.clone()
+    del X
+    assert ab.clapack_potrf("d", ColMajor, uplo, n, A, n) == 0
+    Fcm = A.T                                    # column-major view of the result
+    if uplo == Lower:
+        L = torch.tril(Fcm); R = L @ L.T
+    else:
+        U = torch.triu(Fcm); R = U.T @ U
+    R -= A0.T
+    nrm = torch.max(torch.sum(torch.abs(R), dim=0)).item() / (torch.max(torch.sum(torch.abs(A0), dim=0)).item() * 2.0 ** -52 * n)
+    assert nrm < LATHRESH, nrm
+    other = torch.triu(Fcm, 1) if uplo == Lower else torch.tril(Fcm, -1)
+    other0 = torch.triu(A0.T, 1) if uplo == Lower else torch.tril(A0.T, -1)
+    assert torch.equal(other, other0), "the other triangle was written"
+
+
+# ------------------------------------------------------------------ s/c tensor-core GEMM under gemmtst's element-wise bound
+@pytest.mark.parametrize("pre,M,N,K,ta,tb,alpha,beta", [
+    ("s", 1024, 768, 8192, NoTrans, NoTrans, 1.0, 1.0),
+    ("s", 512, 640, 16384, Trans, NoTrans, -1.1, 0.7),
+    ("s", 2048, 2048, 8192, NoTrans, Trans, 1.0, 0.0),
+    ("c", 512, 384, 8192, NoTrans, NoTrans, 1.0, 1.0),
+    ("c", 384, 512, 8192, ConjTrans, Trans, complex(0.7, -0.4), complex(-1.1, 0.3)),
+])
+def test_tensor_core_gemm_elementwise_gemmtst_bound(pre, M, N, K, ta, tb, alpha, beta):
+    import torch
+    cplx = CPLX[pre]
+    dt = torch.complex64 if cplx else torch.float32
+    wd = torch.complex128 if cplx else torch.float64
+    g = torch.Generator(device="cuda"); g.manual_seed(5)
+
+    def rnd(r, c):           # column-major r x c stored as torch (c, r); uniform(-0.5, 0.5) like the tester's generator
+        if cplx:
+            return torch.complex(torch.rand((c, r), device="cuda", generator=g) - 0.5, torch.rand((c, r), device="cuda", generator=g) - 0.5)
+        return torch.rand((c, r), device="cuda", dtype=dt, generator=g) - 0.5
+    ra, ca = (M, K) if ta == NoTrans else (K, M)
+    rb, cb = (K, N) if tb == NoTrans else (N, K)
+    A, B, Cm = rnd(ra, ca), rnd(rb, cb), rnd(M, N)
+    C0 = Cm.clone()
+    ab.cblas_gemm(pre, ColMajor, ta, tb, M, N, K, alpha, A, ra, B, rb, beta, Cm, M)
+
+    def op(Xt, t):           # torch (c, r) tensor -> column-major op(X) as a torch matrix
+        X = Xt.T.to(wd)
+        return X if t == NoTrans else (X.T if t == Trans else X.conj().T)
+    ref = alpha * (op(A, ta) @ op(B, tb)) + beta * C0.T.to(wd)
+    eps = eps_of(pre)
+    if cplx:
+        a1 = abs(complex(alpha).real) + abs(complex(alpha).imag); b1 = abs(complex(beta).real) + abs(complex(beta).imag)
+        ferr = 2.0 * (a1 * 8.0 * K * eps + b1 * eps) + eps
+        diff = Cm.T.to(wd) - ref
+        worst = max(torch.max(torch.abs(diff.real)).item(), torch.max(torch.abs(diff.imag)).item())
+    else:
+        ferr = 2.0 * (abs(alpha) * 2.0 * K * eps + abs(beta) * eps) + eps
+        worst = torch.max(torch.abs(Cm.T.to(wd) - ref)).item()
+    assert worst <= ferr, (pre, M, N, K, worst, ferr)
+    # normwise (l3blastst) beside it
+    n1 = lambda X: torch.max(torch.sum(torch.abs(X), dim=0)).item()
+    resid = n1(Cm.T.to(wd) - ref) / (max(n1(op(A, ta)), 1) * max(n1(op(B, tb)), 1) * max(n1(C0.T.to(wd)), 1) * eps * max(M, N, K))
+    assert resid < 5.0, resid
+    print(f"{pre}gemm K={K}: worst element error {worst:.3e} (gemmtst bound {ferr:.3e}), normwise resid {resid:.3g}")
+
+
+# ------------------------------------------------------------------ F77 entry points, numerically
+def _I(v):
+    return C.byref(C.c_int(v))
+
+
+def _vp(a):
+    return C.c_void_p(a.ctypes.data)
+
+
+def test_f77_numeric_results_match_oracle(oracle):
+    L = ab.lib()
+    M, N, K = 130, 77, 95
+    one = C.c_size_t(1)
+    # dgemm_('T','N')
+    A = oracle.gegen("d", K, M, K, 1); B = oracle.gegen("d", K, N, K, 2); C0 = oracle.gegen("d", M, N, M, 3)
+    want, got = C0.copy(order="F"), C0.copy(order="F")
+    oracle.gemm("d", Trans, NoTrans, M, N, K, -1.1, A, B, 0.7, want)
+    al, be = C.c_double(-1.1), C.c_double(0.7)
+    L.dgemm_(b"T", b"N", _I(M), _I(N), _I(K), C.byref(al), _vp(A), _I(K), _vp(B), _I(K), C.byref(be), _vp(got), _I(M), one, one)
+    r = _nrm1(got - want) / (max(_nrm1(A), 1) * max(_nrm1(B), 1) * max(_nrm1(C0), 1) * eps_of("d") * max(M, N, K))
+    assert r < 5.0, r
+    # dsyrk_('L','N')
+    A = oracle.gegen("d", N, K, N, 4); C0 = oracle.gegen("d", N, N, N, 5)
+    want, got = C0.copy(order="F"), C0.copy(order="F")
+    oracle.syrk("d", Lower, NoTrans, N, K, 0.7, A, 1.3, want)
+    al, be = C.c_double(0.7), C.c_double(1.3)
+    L.dsyrk_(b"L", b"N", _I(N), _I(K), C.byref(al), _vp(A), _I(N), C.byref(be), _vp(got), _I(N), one, one)
+    assert _nrm1(got - want) / (max(_nrm1(C0), 1) * max(_nrm1(A), 1) * eps_of("d") * max(N, K)) < 5.0
+    assert np.array_equal(np.triu(got, 1), np.triu(C0, 1))
+    # dtrsm_('R','U','T','N')
+    A = oracle.gegen("d", N, N, N, 6); oracle.trddom("d", Upper, N, A)
+    B0 = oracle.gegen("d", M, N, M, 7)
+    want, got = B0.copy(order="F"), B0.copy(order="F")
+    oracle.trsm("d", Right, Upper, Trans, NonUnit, M, N, 0.7, A, want)
+    al = C.c_double(0.7)
+    L.dtrsm_(b"R", b"U", b"T", b"N", _I(M), _I(N), C.byref(al), _vp(A), _I(N), _vp(got), _I(M), one, one, one, one)
+    assert _nrm1(got - want) / (max(oracle.trnrm1("d", Upper, NonUnit, N, A), 1) * max(_nrm1(B0), 1) * eps_of("d") * max(M, N)) < 5.0
+    # dgetrf_: pivots are 1-based (the reference adds 1 in ATL_F77wrap_getrf, atlas-ilp.base:160)
+    n = 300
+    A0 = oracle.gegen("d", n, n, n, n * n + n)
+    want, got = A0.copy(order="F"), A0.copy(order="F")
+    iw, pw = oracle.getrf("d", n, n, want)
+    piv = np.zeros(n, dtype=np.int32); info = C.c_int(-99)
+    L.dgetrf_(_I(n), _I(n), _vp(got), _I(n), _vp(piv), C.byref(info))
+    assert info.value == 0 == iw
+    assert np.array_equal(piv, pw + 1), "dgetrf_ pivots must be 1-based"
+    assert lu_resid("d", n, n, A0, got, piv - 1) < LATHRESH
+    # zgetrf_ too (complex goes through another instantiation)
+    A0 = oracle.gegen("z", n, n, n, 17)
+    want, got = A0.copy(order="F"), A0.copy(order="F")
+    iw, pw = oracle.getrf("z", n, n, want)
+    L.zgetrf_(_I(n), _I(n), _vp(got), _I(n), _vp(piv), C.byref(info))
+    assert info.value == 0 and np.array_equal(piv, pw + 1)
+    # dpotrf_('U') and a non-positive-definite case: info = order of the failing minor
+    S0 = lltgen(oracle, "d", Upper, n, n, 9)
+    want, got = S0.copy(order="F"), S0.copy(order="F")
+    assert oracle.potrf("d", Upper, n, want) == 0
+    L.dpotrf_(b"U", _I(n), _vp(got), _I(n), C.byref(info), one)
+    assert info.value == 0
+    assert llt_resid("d", Upper, n, S0, got) < LATHRESH
+    S0[41, 41] = -1.0
+    got = S0.copy(order="F")
+    L.dpotrf_(b"U", _I(n), _vp(got), _I(n), C.byref(info), one)
+    assert info.value == 42

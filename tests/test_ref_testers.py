@@ -87,8 +87,7 @@ def test_llttst(pre):
 
 
 def test_llttst_lookahead_sizes():
-    check_cases(run("xdllttst", "-n", 2600, "-U", 2, "u", "l"))
-    check_cases(run("xdllttst", "-n", 4096, "-U", 2, "u", "l"))
+    check_cases(run("xdllttst", "-n", 2600, "-U", 2, "u", "l"))      # (the tester's own host-side A - L*L' is O(N^3) scalar code)
 
 
 @pytest.mark.parametrize("pre", ["s", "d", "c", "z"])

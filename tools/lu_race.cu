@@ -39,6 +39,7 @@ __global__ void cks_kernel(const double* A, size_t total, unsigned long long* ou
 
 typedef void (*getrf_fn)(int, int, void*, size_t, int*, int*);
 typedef void (*potrf_fn)(int, int, void*, size_t, int*);
+typedef void (*gemm_fn)(int, int, size_t, size_t, size_t, double, const double*, size_t, const double*, size_t, double, double*, size_t);
 
 int main(int argc, char** argv) {
   if (argc < 4) { fprintf(stderr, "usage: %s lib.so N reps [getrf|potrf]\n", argv[0]); return 2; }
@@ -49,6 +50,26 @@ int main(int argc, char** argv) {
   getrf_fn getrf = (getrf_fn)dlsym(h, "atlb200_dgetrf_dev");
   potrf_fn potrff = (potrf_fn)dlsym(h, "atlb200_dpotrf_dev");
   if (!getrf || !potrff) { fprintf(stderr, "missing entry points\n"); return 2; }
+  if (argc > 4 && !strcmp(argv[4], "gemm")) {   // DGEMM NN rate on device-resident operands through ATL_dgemm
+    gemm_fn gemm = (gemm_fn)dlsym(h, "ATL_dgemm");
+    const size_t tot = (size_t)n * n;
+    double *A, *B, *C;
+    CK(cudaMalloc(&A, tot * 8)); CK(cudaMalloc(&B, tot * 8)); CK(cudaMalloc(&C, tot * 8));
+    fill_kernel<<<1024, 256>>>(A, n, n, 0); fill_kernel<<<1024, 256>>>(B, n, n, 0); fill_kernel<<<1024, 256>>>(C, n, n, 0);
+    CK(cudaDeviceSynchronize());
+    cudaEvent_t e0, e1; CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+    float best = 1e30f, sum = 0;
+    for (int it = 0; it < reps + 1; it++) {
+      CK(cudaEventRecord(e0, 0));
+      gemm(111, 111, n, n, n, 1.0, A, n, B, n, 1.0, C, n);
+      CK(cudaEventRecord(e1, 0)); CK(cudaDeviceSynchronize());
+      float ms; CK(cudaEventElapsedTime(&ms, e0, e1));
+      if (it) { sum += ms; if (ms < best) best = ms; }
+    }
+    printf("RESULT gemm n=%d reps=%d best_ms=%.3f best_tflops=%.2f mean_tflops=%.2f\n", n, reps, best, 2.0 * n * n * n / best * 1e-9,
+           2.0 * n * n * n / (sum / reps) * 1e-9);
+    return 0;
+  }
   const size_t ld = (size_t)n, total = ld * n;
   double *A0, *A; int *piv, *info; unsigned long long* dck;
   CK(cudaMalloc(&A0, total * 8)); CK(cudaMalloc(&A, total * 8));
