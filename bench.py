@@ -49,7 +49,7 @@ def cpu_dgemm(n, cols_per_thread, steps, warmup, threads=None):
     import numpy as np
     from oracle import orc
     try:
-        ref = orc.Ref(); kind = "reference"
+        ref = orc.Ref(); kind = "untuned-reference"      # the reference's own C, but its triple-loop BLAS, not the tuned amm GEMM
         fn = ref.lib.ATL_drefgemm
         fn.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, C.c_void_p, C.c_int, C.c_void_p, C.c_int,
                        C.c_double, C.c_void_p, C.c_int]
@@ -99,8 +99,8 @@ def run_reference(args):
         "warmup": args.warmup, "ms_per_step": round(dt * 1e3, 3), "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": f"cblas_dgemm M=N=K={n} NoTrans/NoTrans column-major alpha=beta=1", "cpu_impl":
-                   "ATL_drefgemm (reference trusted BLAS, oracle/_ref)" if kind == "reference" else "oracle port (orc_dgemm)",
-                   "note": "tuned ATLAS (empirical-search build) is unbuildable here, see DESIGN.md"},
+                   "ATL_drefgemm (reference trusted BLAS, oracle/_ref)" if kind != "port" else "oracle port (orc_dgemm)",
+                   "note": "UNTUNED: the tuned ATLAS build aborts in its own search (DoSyrkAmmUR assertion, BASELINE.md); read ratios against this arm as upper bounds"},
         "cpu_baseline": {"value": round(g, 3), "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
         "e2e": {"value": round(g, 3), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
@@ -148,6 +148,77 @@ class ClockSampler:
         return {"sm_mhz": hot[len(hot) // 2] if hot else None, "sm_max_mhz": mx[0] if mx else None,
                 "reasons": sorted(reasons), "samples": len(sm)}
 
+
+
+def run_big_factorizations(args, torch, dist, ab, dev, rank, world, barrier, max_over_ranks, peak_all=None):
+    """DGETRF and DPOTRF (Lower) at N = args.big_size (65536): single GPU through clapack_* on device-resident data, N GPUs
+    through math_atlas_b200.dist (block-cyclic column panels, NCCL panel broadcast).  One warm-up at a quarter of the
+    size, one timed run each (a run is seconds).  Returns {"dgetrf_n65536": {...}, "dpotrf_n65536": {...}}."""
+    from math_atlas_b200 import dist as abd
+    n = args.big_size
+    out = {}
+    lu_flops = float(n) ** 3 - float(n) ** 3 / 3.0 - float(n) * n / 2.0      # reference lutst.c:268
+    llt_flops = float(n) ** 3 / 3.0 + float(n) * n / 2.0                      # reference llttst (atlas-tlp.base:1542)
+    nb = 512
+    gen = torch.Generator(device=dev)
+
+    def fill(t, seed):
+        gen.manual_seed(seed)
+        rows = t.shape[0]
+        step = max(1, (1 << 28) // max(t.shape[1], 1))
+        for r0 in range(0, rows, step):                # in place, chunked: no second 32 GiB temporary
+            t[r0:r0 + step].uniform_(-0.5, 0.5, generator=gen)
+
+    if world == 1:
+        A = torch.empty((n, n), dtype=torch.float64, device=dev)
+        piv = torch.zeros(n, dtype=torch.int32, device=dev)
+        W = torch.empty((n // 4, n // 4), dtype=torch.float64, device=dev); fill(W, 3)
+        ab.clapack_dgetrf(ab.CblasColMajor, n // 4, n // 4, W, n // 4, piv)           # warm-up (module load, probes)
+        del W
+        for what in ("dgetrf", "dpotrf"):
+            fill(A, 11)
+            if what == "dpotrf":
+                A.diagonal().add_(0.3 * n)           # the lower triangle of a diagonally dominant symmetric matrix
+            torch.cuda.synchronize()
+            a0 = torch.cuda.Event(enable_timing=True); a1 = torch.cuda.Event(enable_timing=True)
+            ab.reset_launch_count()
+            a0.record()
+            info = ab.clapack_dgetrf(ab.CblasColMajor, n, n, A, n, piv) if what == "dgetrf" else ab.clapack_dpotrf(ab.CblasColMajor, ab.CblasLower, n, A, n)
+            a1.record(); torch.cuda.synchronize()
+            ms = a0.elapsed_time(a1)
+            fl = lu_flops if what == "dgetrf" else llt_flops
+            out[f"{what}_n{n}"] = {"value": round(fl / (ms * 1e-3) * 1e-9, 1), "unit": UNIT, "ms": round(ms, 2), "info": int(info),
+                                   "n_gpus": 1, "launches": int(ab.launch_count()), "distribution": "single GPU, look-ahead NB=512"}
+        del A
+        return out
+    lay = abd.BlockCyclic1D(n, nb, world, rank)
+    ops = abd.CudaOps("d")
+    loc = torch.empty((lay.ncols_local, n), dtype=torch.float64, device=dev)
+    for what in ("dgetrf", "dpotrf"):
+        for kb in lay.my_blocks:
+            gen.manual_seed(5000 + kb)
+            blk = loc[lay.local_col(kb):lay.local_col(kb) + lay.width(kb)]
+            blk.uniform_(-0.5, 0.5, generator=gen)
+            if what == "dpotrf":
+                c0 = lay.start(kb)
+                idx = torch.arange(lay.width(kb), device=dev)
+                blk[idx, c0 + idx] += 0.3 * n
+        barrier()
+        a0 = torch.cuda.Event(enable_timing=True); a1 = torch.cuda.Event(enable_timing=True)
+        a0.record()
+        if what == "dgetrf":
+            _, info = abd.pgetrf("d", n, lay, loc, n, ops)
+        else:
+            info = abd.ppotrf("d", lay, loc, n, ops)
+        a1.record()
+        barrier()
+        ms = max_over_ranks(a0.elapsed_time(a1))
+        fl = lu_flops if what == "dgetrf" else llt_flops
+        out[f"{what}_n{n}"] = {"value": round(fl / (ms * 1e-3) * 1e-9, 1), "unit": UNIT, "ms": round(ms, 2), "info": int(info), "n_gpus": world,
+                               "distribution": f"block-cyclic column panels nb={nb} over 1x{world} GPUs, one NCCL broadcast per panel, look-ahead"}
+    ops.close()
+    del loc
+    return out
 
 # ------------------------------------------------------------------------------------------------
 # our arm
@@ -215,15 +286,25 @@ def run_ours(args):
     ms_per_step = total_ms / args.steps
     value = flops_total / (ms_per_step * 1e-3) * 1e-9
 
-    # ---- e2e: host (pinned) buffers through the same C-ABI call ----
+    # ---- e2e: host (pinned) buffers through the public API ----
+    # 1 GPU: cblas_dgemm with three host pointers (the library pipelines H2D / GEMM / D2H by column panels).
+    # N GPUs: every rank holds the whole problem in host memory (it is the same matrix everywhere), uploads only ITS 1/N
+    # of A over PCIe and the ranks all-gather A over NVLink (math_atlas_b200.dist.pgemm_host), then each computes its
+    # column slab of C from host B/C slabs.  Round 1 uploaded all of A on every rank: 2 GiB x N through the host, which is
+    # what held the 8-GPU end-to-end number at 0.21 efficiency.
+    from math_atlas_b200 import dist as abd
     hA = torch.empty((n, n), dtype=torch.float64).pin_memory(); hA.copy_(A)
     hB = torch.empty((nloc, n), dtype=torch.float64).pin_memory(); hB.copy_(B)
     hC = torch.empty((nloc, n), dtype=torch.float64).pin_memory(); hC.copy_(Cm)
+    dA_e2e = torch.empty((n, n), dtype=torch.float64, device=dev) if world > 1 else None
     torch.cuda.synchronize()
 
     def step_host():
-        ab.cblas_dgemm(ab.CblasColMajor, ab.CblasNoTrans, ab.CblasNoTrans, n, nloc, n, 1.0, hA.data_ptr(), n, hB.data_ptr(), n, 1.0,
-                       hC.data_ptr(), n)
+        if world == 1:
+            ab.cblas_dgemm(ab.CblasColMajor, ab.CblasNoTrans, ab.CblasNoTrans, n, nloc, n, 1.0, hA.data_ptr(), n, hB.data_ptr(), n, 1.0,
+                           hC.data_ptr(), n)
+        else:
+            abd.pgemm_host("d", n, nloc, n, 1.0, hA, n, hB, n, 1.0, hC, n, dA_e2e, rank, world)
     e2e_steps = max(2, min(args.steps, 4))
     step_host()
     barrier()
@@ -235,8 +316,8 @@ def run_ours(args):
     barrier()
     e2e_ms = max_over_ranks(e0.elapsed_time(e1)) / e2e_steps
     e2e_val = flops_total / (e2e_ms * 1e-3) * 1e-9
-    h2d = 8 * (n * n + 2 * n * nloc); d2h = 8 * n * nloc
-    del hA, hB, hC
+    h2d = 8 * (n * n // world + 2 * n * nloc) * world; d2h = 8 * n * nloc * world     # all ranks together, per step
+    del hA, hB, hC, dA_e2e
 
     # ---- DGETRF at the same N (single GPU, device-resident) ----
     dgetrf = None
@@ -290,6 +371,11 @@ def run_ours(args):
                   "frac_of_fp64_peak": round(lu_flops / (best * 1e-3) * 1e-12 / (peak * world), 4) if peak else None}
         del loc
 
+    # ---- BASELINE configs 4 and 5: DPOTRF / DGETRF N = 65536 on 1/2/4/8 GPUs (driver-measured) ----
+    big = None
+    if not args.no_big:
+        big = run_big_factorizations(args, torch, dist, ab, dev, rank, world, barrier, max_over_ranks, peak_all=None)
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -336,6 +422,11 @@ def run_ours(args):
         line["cpu_baseline"] = cpu
     if dgetrf is not None:
         line["dgetrf"] = dgetrf
+    if big:
+        for kname, v in big.items():
+            if peak and isinstance(v, dict) and v.get("value"):
+                v["frac_of_fp64_peak"] = round(v["value"] * 1e-3 / (peak * world), 4)
+            line[kname] = v
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -350,6 +441,8 @@ def main():
     ap.add_argument("--size", type=int, default=16384)
     ap.add_argument("--no-getrf", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-big", action="store_true", help="skip the N=65536 DGETRF/DPOTRF keys")
+    ap.add_argument("--big-size", type=int, default=65536)
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

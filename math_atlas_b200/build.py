@@ -32,7 +32,7 @@ VARIANTS = {
     "diag": (["-DATLB200_DIAG"], []),                      # look-ahead race diagnostics (csrc/lu_diag.cuh)
     "nofence": (["-DAB_RELEASE_FENCE=0"], []),              # stage release by data dependency only
     "cg": (["-Xptxas", "-dlcm=cg"], []),                    # round-1 mitigation (global loads bypass L1), for comparison
-    "rel2": (["-DAB_RELEASE_MODE=2"], []),                  # dependent arrive, predicated, no fence
+    "rel1": (["-DAB_RELEASE_MODE=1"], []),                  # lane-0 branch + fence.proxy.async + dependent arrive
     "rel3": (["-DAB_RELEASE_MODE=3"], []),                  # ... issued one k-group into the next stage
     "oldrelease": (["-DAB_RELEASE_OLD=1"], []),             # the round-1 stage release (racy), to measure what the fix costs
 }

@@ -21,6 +21,7 @@
 #include <mutex>
 #include <memory>
 #include <algorithm>
+#include <vector>
 
 using namespace ab;
 
@@ -262,10 +263,121 @@ static bool atl_gemm_pipelined(int TA, int TB, size_t M, size_t N, size_t K, T a
   return true;
 }
 
+// ---- one call, several GPUs (the role of the reference's pthread ATL_tgemm, Clint/atlas-thr.base:5197, behind the SAME entry
+// points) --------------------------------------------------------------------------------------------------------------------
+// Opt-in: ATLB200_DEVICES=<n> (or atlb200_set_devices(n)) lets a host-pointer GEMM that is large enough fan out over the
+// first n visible devices from the calling thread: C and B are cut into n column slabs (never K: no reduction, the
+// reference's ATL_thrdecompMM splits M/N only); device d uploads ITS 1/n of A over PCIe, the devices exchange the parts by
+// peer copies over NVLink (an all-gather), each computes its slab and copies it back.  Off by default because one-process-
+// per-GPU programs (torchrun, MPI) see all devices from every rank.
+namespace {
+int g_devices = -1;      // -1: read ATLB200_DEVICES on first use
+struct DevCtx { cudaStream_t st = nullptr; cudaEvent_t part = nullptr; bool peers = false; };
+DevCtx g_dev[AB_MAX_DEV];
+std::mutex g_multi_mu;
+int multi_devices() {
+  if (g_devices < 0) { const char* v = getenv("ATLB200_DEVICES"); g_devices = v ? atoi(v) : 1; }
+  int n = 0;
+  if (g_devices <= 1 || cudaGetDeviceCount(&n) != cudaSuccess) return 1;
+  return std::min(std::min(g_devices, n), AB_MAX_DEV);
+}
+}  // namespace
+extern "C" void atlb200_set_devices(int n) { g_devices = n < 1 ? 1 : n; }
+
+template <typename T>
+static bool atl_gemm_multi(int TA, int TB, size_t M, size_t N, size_t K, T alpha, const T* A, size_t lda, const T* B, size_t ldb,
+                           T beta, T* C, size_t ldc) {
+  const int D = multi_devices();
+  if (D <= 1 || g_async) return false;
+  if (is_device_ptr(A) || is_device_ptr(B) || is_device_ptr(C)) return false;
+  if (ST<T>::is_zero(alpha) || K == 0) return false;
+  if ((double)M * N * K < 4096.0 * 4096.0 * 4096.0 || N < (size_t)256 * D) return false;
+  std::lock_guard<std::mutex> lock(g_multi_mu);
+  const bool tA = (TA == TransT || TA == ConjTrans), tB = (TB == TransT || TB == ConjTrans);
+  const bool beta0 = ST<T>::is_zero(beta);
+  const size_t esz = sizeof(T);
+  int home = 0;
+  AB_CUDA_CHECK(cudaGetDevice(&home));
+  cudaStream_t home_stream = current_stream();
+  // stored A: ra x ca, columns split into D contiguous parts (any split of the storage will do for the all-gather)
+  const size_t ra = tA ? K : M, ca = tA ? M : K;
+  const size_t lda_d = (ra + 15) & ~(size_t)15;
+  auto part0 = [&](int d) { return (ca * (size_t)d) / D; };
+  // C/B slabs: multiples of 128 columns
+  const size_t per = (((N + D - 1) / D) + 127) / 128 * 128;
+  std::vector<T*> dA(D, nullptr), dB(D, nullptr), dC(D, nullptr);
+  const size_t rb = tB ? N : K;          // rows of stored B (for tB the slab is a row range of the stored matrix)
+  for (int d = 0; d < D; d++) {
+    AB_CUDA_CHECK(cudaSetDevice(d));
+    DevCtx& cx = g_dev[d];
+    if (!cx.st) {
+      AB_CUDA_CHECK(cudaStreamCreateWithFlags(&cx.st, cudaStreamNonBlocking));
+      AB_CUDA_CHECK(cudaEventCreateWithFlags(&cx.part, cudaEventDisableTiming));
+    }
+    if (!cx.peers) {
+      for (int p = 0; p < D; p++)
+        if (p != d) { int can = 0; cudaDeviceCanAccessPeer(&can, d, p); if (can && cudaDeviceEnablePeerAccess(p, 0) != cudaSuccess) (void)cudaGetLastError(); }
+      cx.peers = true;
+    }
+    keep_pool_cached();
+    const size_t c0 = std::min(N, per * d), nc = std::min(per, N - c0);
+    AB_CUDA_CHECK(cudaMallocAsync(&dA[d], esz * lda_d * ca, cx.st));
+    if (nc == 0) continue;
+    // this device's part of A
+    const size_t a0 = part0(d), a1 = part0(d + 1);
+    if (a1 > a0)
+      AB_CUDA_CHECK(cudaMemcpy2DAsync(dA[d] + a0 * lda_d, esz * lda_d, A + a0 * lda, esz * lda, esz * ra, a1 - a0, cudaMemcpyHostToDevice, cx.st));
+    AB_CUDA_CHECK(cudaEventRecord(cx.part, cx.st));
+    // B and C slabs
+    const size_t ldb_d = (((tB ? nc : K) + 15) & ~(size_t)15), ldc_d = (M + 15) & ~(size_t)15;
+    AB_CUDA_CHECK(cudaMallocAsync(&dB[d], esz * ldb_d * (tB ? K : nc), cx.st));
+    AB_CUDA_CHECK(cudaMallocAsync(&dC[d], esz * ldc_d * nc, cx.st));
+    if (!tB) AB_CUDA_CHECK(cudaMemcpy2DAsync(dB[d], esz * ldb_d, B + c0 * ldb, esz * ldb, esz * K, nc, cudaMemcpyHostToDevice, cx.st));
+    else     AB_CUDA_CHECK(cudaMemcpy2DAsync(dB[d], esz * ldb_d, B + c0, esz * ldb, esz * nc, K, cudaMemcpyHostToDevice, cx.st));
+    if (!beta0) AB_CUDA_CHECK(cudaMemcpy2DAsync(dC[d], esz * ldc_d, C + c0 * ldc, esz * ldc, esz * M, nc, cudaMemcpyHostToDevice, cx.st));
+    (void)rb;
+  }
+  for (int d = 0; d < D; d++) {
+    const size_t c0 = std::min(N, per * d), nc = std::min(per, N - c0);
+    if (nc == 0) continue;
+    AB_CUDA_CHECK(cudaSetDevice(d));
+    DevCtx& cx = g_dev[d];
+    // all-gather of A: pull every other device's part over NVLink
+    for (int q = 1; q < D; q++) {
+      const int p = (d + q) % D;
+      const size_t a0 = part0(p), a1 = part0(p + 1);
+      const size_t pc0 = std::min(N, per * p);
+      if (a1 == a0 || std::min(per, N - pc0) == 0) {
+        // a device without a slab uploaded nothing: take that part from the host instead
+        if (a1 > a0) AB_CUDA_CHECK(cudaMemcpy2DAsync(dA[d] + a0 * lda_d, esz * lda_d, A + a0 * lda, esz * lda, esz * ra, a1 - a0, cudaMemcpyHostToDevice, cx.st));
+        continue;
+      }
+      AB_CUDA_CHECK(cudaStreamWaitEvent(cx.st, g_dev[p].part, 0));
+      AB_CUDA_CHECK(cudaMemcpyPeerAsync(dA[d] + a0 * lda_d, d, dA[p] + a0 * lda_d, p, esz * lda_d * (a1 - a0), cx.st));
+    }
+    const size_t ldb_d = (((tB ? nc : K) + 15) & ~(size_t)15), ldc_d = (M + 15) & ~(size_t)15;
+    set_current_stream(cx.st);
+    gemm<T>(TA, TB, (int)M, (int)nc, (int)K, alpha, dA[d], lda_d, dB[d], ldb_d, beta, dC[d], ldc_d);
+    AB_CUDA_CHECK(cudaMemcpy2DAsync(C + c0 * ldc, esz * ldc, dC[d], esz * ldc_d, esz * M, nc, cudaMemcpyDeviceToHost, cx.st));
+  }
+  // a peer may still be reading this device's part of A: free only after everybody has finished
+  for (int d = 0; d < D; d++) { AB_CUDA_CHECK(cudaSetDevice(d)); AB_CUDA_CHECK(cudaStreamSynchronize(g_dev[d].st)); }
+  for (int d = 0; d < D; d++) {
+    AB_CUDA_CHECK(cudaSetDevice(d));
+    if (dA[d]) AB_CUDA_CHECK(cudaFreeAsync(dA[d], g_dev[d].st));
+    if (dB[d]) AB_CUDA_CHECK(cudaFreeAsync(dB[d], g_dev[d].st));
+    if (dC[d]) AB_CUDA_CHECK(cudaFreeAsync(dC[d], g_dev[d].st));
+  }
+  AB_CUDA_CHECK(cudaSetDevice(home));
+  set_current_stream(home_stream);
+  return true;
+}
+
 template <typename T>
 static void atl_gemm(int TA, int TB, size_t M, size_t N, size_t K, T alpha, const T* A, size_t lda, const T* B, size_t ldb,
                      T beta, T* C, size_t ldc) {
   if (M == 0 || N == 0) return;
+  if (atl_gemm_multi<T>(TA, TB, M, N, K, alpha, A, lda, B, ldb, beta, C, ldc)) return;
   if (atl_gemm_pipelined<T>(TA, TB, M, N, K, alpha, A, lda, B, ldb, beta, C, ldc)) return;
   const bool needAB = !(ST<T>::is_zero(alpha) || K == 0);
   const bool tA = (TA == TransT || TA == ConjTrans), tB = (TB == TransT || TB == ConjTrans);

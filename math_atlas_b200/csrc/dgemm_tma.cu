@@ -35,11 +35,17 @@ int gemm_cta_cap();
 
 namespace {
 
-constexpr int BM = 128, BN = 128, BK = 16, STAGES = 6;
-constexpr int A_TILE_BYTES = BM * BK * 8, B_TILE_BYTES = BN * BK * 8;
-constexpr int STAGE_BYTES = A_TILE_BYTES + B_TILE_BYTES;
+// Tile: 128 rows x BN columns, BN = 32*NI with NI = 4 (128 x 128, the default) or 2 (128 x 64: small and skinny problems
+// whose 128 x 128 tiles would leave most SMs idle - the reference's ammm_IP / tN special cases, atlas-ammm.base:16370-16991).
+constexpr int BM = 128, BK = 16, STAGES = 6;
+constexpr int A_TILE_BYTES = BM * BK * 8;
+template <int NI> struct TileN {
+  static constexpr int BN = 32 * NI;
+  static constexpr int B_TILE_BYTES = BN * BK * 8;
+  static constexpr int STAGE_BYTES = A_TILE_BYTES + B_TILE_BYTES;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 2 * STAGES * 8 + STAGES * 4 /*tile ring*/;
+};
 constexpr int CONS_WARPS = 8, THREADS = (CONS_WARPS + 1) * 32;
-constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 2 * STAGES * 8 + STAGES * 4 /*tile ring*/;
 constexpr int GROUP_M = 16;  // tile rasterisation group (L2 reuse of the B panel)
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
@@ -64,12 +70,16 @@ __device__ __forceinline__ void mbar_arrive(uint32_t a) {
 //    one A fragment (8 rows x 4 k) of one warp came from k-tile kt+STAGES, a 256-element error in C.
 //    `dep` carries the low words of the stage's last fragments ANDed with a run-time zero, so the arrive's
 //    address depends on every one of them and cannot issue before they are in registers;
-//  * fence.proxy.async orders the generic-proxy reads before the async-proxy writes that the arrive licenses.
-// AB_RELEASE_MODE (measurement variants, build.py VARIANTS): 1 = fence + dependent arrive at the end of the stage
-// (default), 2 = dependent arrive only, predicated on lane 0 (no branch, no fence), 3 = as 2 but issued one k-group into
-// the NEXT stage, between its DMMAs, so that the stage boundary carries no extra instructions.
+//  (fence.proxy.async before the arrive was tried as well - AB_RELEASE_MODE 1 - and is not needed once the arrive
+//   waits for the data: see the mode table below.)
+// AB_RELEASE_MODE (build.py VARIANTS; profiles/r02_dgemm_release_modes.txt): 2 (default) = the dependent arrive alone,
+// predicated on lane 0 - once the loads are in registers the read is complete, the arrive is a release and the producer's
+// wait an acquire, so the later TMA write cannot overtake it; 36.2 TFLOP/s at N=16384, the same as the racy original,
+// and 0 differing runs in the forced stress test.  1 = lane-0 branch + fence.proxy.async + dependent arrive (the first
+// fix: -1 %, the branch and MEMBAR sit on the stage boundary of all eight warps at once); 3 = as 2 but issued one
+// k-group into the next stage (no gain over 2).
 #ifndef AB_RELEASE_MODE
-#define AB_RELEASE_MODE 1
+#define AB_RELEASE_MODE 2
 #endif
 __device__ __forceinline__ void mbar_release_lane0(uint32_t a, uint32_t dep, int lane) {
   asm volatile("{\n\t.reg .pred p;\n\tsetp.eq.s32 p, %1, 0;\n\t@p mbarrier.arrive.shared::cta.b64 _, [%0];\n\t}" ::"r"(a + dep), "r"(lane) : "memory");
@@ -119,6 +129,7 @@ __host__ __device__ constexpr uint32_t xm(int j, int hi8) {
 }
 
 // tile index -> tile coordinates (grouped rasterisation: GROUP_M tile rows share their B panel in L2)
+template <int BN>
 __device__ __forceinline__ void tile_coords(int tile, int tiles_m, int tiles_n, int& m0, int& n0) {
   const int in_group = GROUP_M * tiles_n;
   const int first_m = (tile / in_group) * GROUP_M;
@@ -126,6 +137,7 @@ __device__ __forceinline__ void tile_coords(int tile, int tiles_m, int tiles_n, 
   m0 = (first_m + (tile % in_group) % gsz) * BM;
   n0 = ((tile % in_group) / gsz) * BN;
 }
+template <int BN>
 __device__ __forceinline__ bool tile_skipped(int cmode, int m0, int n0) {
   return (cmode == C_UPPER && m0 > n0 + BN - 1) || (cmode == C_LOWER && n0 > m0 + BM - 1);
 }
@@ -144,7 +156,7 @@ __device__ __forceinline__ unsigned my_smid() { unsigned s; asm volatile("mov.u3
 // GEMM leaves one GPC's worth of SMs to the panel kernels (a thread-block cluster needs all its
 // SMs free inside one GPC; a grid that is merely capped leaves scattered SMs and the cluster
 // would wait for the GEMM to finish - measured with tools/cluster_coexist_test.cu).
-template <bool A_KMAJOR, bool B_KMAJOR>
+template <bool A_KMAJOR, bool B_KMAJOR, int NI>
 __global__ void __launch_bounds__(THREADS, 1)
 dgemm_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                  double* __restrict__ C, size_t ldc, int M, int N, int K, double alpha, double beta,
@@ -155,6 +167,8 @@ dgemm_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const unsigned sm = my_smid();
     if ((reserved.w[(sm >> 6) & 3] >> (sm & 63)) & 1ull) return;
   }
+  constexpr int BN = TileN<NI>::BN, B_TILE_BYTES = TileN<NI>::B_TILE_BYTES, STAGE_BYTES = TileN<NI>::STAGE_BYTES;
+  (void)B_TILE_BYTES;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t bar_base = smem_base + STAGES * STAGE_BYTES;  // full[s] at +8s, empty[s] at +8(STAGES+s)
@@ -184,8 +198,8 @@ dgemm_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       const bool done = tile >= ntiles;
       int m0 = 0, n0 = 0;
       if (!done) {
-        tile_coords(tile, tiles_m, tiles_n, m0, n0);
-        if (tile_skipped(cmode, m0, n0)) continue;
+        tile_coords<BN>(tile, tiles_m, tiles_n, m0, n0);
+        if (tile_skipped<BN>(cmode, m0, n0)) continue;
       }
       const int nk = done ? 1 : KT;
       for (int kt = 0; kt < nk; kt++, it++) {
@@ -202,7 +216,7 @@ dgemm_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         if (A_KMAJOR) { if (lane == 0) tma_load_2d(sa, &tmA, k0, m0, full); }
         else          { if (lane < 8) tma_load_2d(sa + lane * 2048, &tmA, m0 + 16 * lane, k0, full); }
         if (B_KMAJOR) { if (lane == 16) tma_load_2d(sb, &tmB, k0, n0, full); }
-        else          { if (lane >= 16 && lane < 24) tma_load_2d(sb + (lane - 16) * 2048, &tmB, n0 + 16 * (lane - 16), k0, full); }
+        else          { if (lane >= 16 && lane < 16 + BN / 16) tma_load_2d(sb + (lane - 16) * 2048, &tmB, n0 + 16 * (lane - 16), k0, full); }
       }
       if (done) break;
     }
@@ -217,7 +231,7 @@ dgemm_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   const uint32_t LK = (uint32_t)g * 128u + ((((base_t >> 1) ^ (uint32_t)g) & 7u) << 4) + ((base_t & 1u) << 3);
   const uint32_t LM = base_t * 128u + (((((uint32_t)g >> 1) ^ (base_t & 7u)) & 7u) << 4) + (((uint32_t)g & 1u) << 3);
   const uint32_t a_lane = A_KMAJOR ? (uint32_t)(wm * 64) * 128u + LK : (uint32_t)(wm * 4) * 2048u + LM;
-  const uint32_t b_lane = B_KMAJOR ? (uint32_t)(wn * 32) * 128u + LK : (uint32_t)(wn * 2) * 2048u + LM;
+  const uint32_t b_lane = B_KMAJOR ? (uint32_t)(wn * 8 * NI) * 128u + LK : (uint32_t)(wn * NI / 2) * 2048u + LM;
   const bool beta0 = (beta == 0.);
   const uint32_t zero_rt = (uint32_t)(ldc >> 63);   // 0 at run time, unknown to the compiler (see mbar_release)
 
@@ -232,25 +246,25 @@ dgemm_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     asm volatile("ld.shared.s32 %0, [%1];" : "=r"(tile) : "r"(ring_base + 4 * (it % STAGES)) : "memory");
     if (tile < 0) break;
     int m0, n0;
-    tile_coords(tile, tiles_m, tiles_n, m0, n0);
+    tile_coords<BN>(tile, tiles_m, tiles_n, m0, n0);
 
     if (!beta0) {
       // bring this tile's C block (128 columns x 1 KiB) into L2 while the k loop runs: thread i of
       // the 256 consumers takes column i/2, half i%2, four 128-byte lines
       const int ctid = (int)threadIdx.x;               // consumer warps are 0..7
       const int pc = n0 + (ctid >> 1), pr = m0 + (ctid & 1) * 64;
-      if (pc < N) {
+      if (pc < N && (ctid >> 1) < BN) {
         const double* cp = C + (size_t)pc * ldc;
 #pragma unroll
         for (int q = 0; q < 4; q++)
           if (pr + q * 16 < M) asm volatile("prefetch.global.L2 [%0];" ::"l"(cp + pr + q * 16));
       }
     }
-    double acc[8][4][2];
+    double acc[8][NI][2];
 #pragma unroll
     for (int i = 0; i < 8; i++)
 #pragma unroll
-      for (int j = 0; j < 4; j++) { acc[i][j][0] = 0.; acc[i][j][1] = 0.; }
+      for (int j = 0; j < NI; j++) { acc[i][j][0] = 0.; acc[i][j][1] = 0.; }
 
 #if AB_RELEASE_MODE == 3
     uint32_t prev_bar = 0, prev_dep = 0;
@@ -266,7 +280,7 @@ dgemm_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 #if AB_RELEASE_MODE == 3
         if (j == 1 && kt > 0) mbar_release_lane0(prev_bar, prev_dep, lane);   // previous stage: its loads returned long ago
 #endif
-        double a[8], b[4];
+        double a[8], b[NI];
 #pragma unroll
         for (int mi = 0; mi < 8; mi++) {
           // K-major: rows advance 8*128 B per mi; MN-major: 16-row group = 2048 B, (mi&1) picks the half
@@ -275,7 +289,7 @@ dgemm_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           a[mi] = lds_f64(sa + off);
         }
 #pragma unroll
-        for (int ni = 0; ni < 4; ni++) {
+        for (int ni = 0; ni < NI; ni++) {
           const uint32_t off = B_KMAJOR ? ((b_lane + ni * 1024u) ^ xk(j))
                                         : (b_lane + (ni >> 1) * 2048u) ^ xm(j, ni & 1);
           b[ni] = lds_f64(sb + off);
@@ -284,12 +298,12 @@ dgemm_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 #pragma unroll
           for (int mi = 0; mi < 8; mi++) dep |= lo32(a[mi]);
 #pragma unroll
-          for (int ni = 0; ni < 4; ni++) dep |= lo32(b[ni]);
+          for (int ni = 0; ni < NI; ni++) dep |= lo32(b[ni]);
         }
 #pragma unroll
         for (int mi = 0; mi < 8; mi++)
 #pragma unroll
-          for (int ni = 0; ni < 4; ni++) dmma884(acc[mi][ni][0], acc[mi][ni][1], a[mi], b[ni]);
+          for (int ni = 0; ni < NI; ni++) dmma884(acc[mi][ni][0], acc[mi][ni][1], a[mi], b[ni]);
       }
 #if AB_RELEASE_MODE == 1
       __syncwarp();
@@ -309,10 +323,10 @@ dgemm_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     // at the start of the tile; from DRAM they cost 9.6 us per tile, 12 % of a K=512 update.
     const bool interior = (cmode == C_FULL) && (m0 + BM <= M) && (n0 + BN <= N);
 #pragma unroll
-    for (int ni = 0; ni < 4; ni++) {
+    for (int ni = 0; ni < NI; ni++) {
 #pragma unroll
       for (int e = 0; e < 2; e++) {
-        const int n = n0 + wn * 32 + ni * 8 + 2 * t + e;
+        const int n = n0 + wn * 8 * NI + ni * 8 + 2 * t + e;
         if (interior) {                      // no per-element tests: the eight loads of a column go out together
           double* cc = C + (size_t)n * ldc + (m0 + wm * 64 + g);
           double c8[8];
@@ -381,12 +395,12 @@ thread_local int* g_counters[AB_MAX_DEV] = {};   // ring of device tile counters
 thread_local int g_counter_next = 0;
 constexpr int NCOUNTERS = 256;
 
-template <bool AK, bool BK_>
+template <bool AK, bool BK_, int NI>
 void launch(const CUtensorMap& ta, const CUtensorMap& tb, double* C, size_t ldc, int M, int N, int K, double alpha,
             double beta, int cmode, const int* abort_flag) {
-  constexpr int smem_req = SMEM_BYTES;
+  constexpr int smem_req = TileN<NI>::SMEM_BYTES, BN = TileN<NI>::BN;
   static PerDeviceOnce attr_once;
-  attr_once([] { AB_CUDA_CHECK(cudaFuncSetAttribute(dgemm_tma_kernel<AK, BK_>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_req)); });
+  attr_once([] { AB_CUDA_CHECK(cudaFuncSetAttribute(dgemm_tma_kernel<AK, BK_, NI>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_req)); });
   const int tiles_m = (M + BM - 1) / BM, tiles_n = (N + BN - 1) / BN;
   int grid = std::min(tiles_m * tiles_n, gemm_cta_cap());
   SmMask mask = {{0, 0, 0, 0}};
@@ -401,10 +415,19 @@ void launch(const CUtensorMap& ta, const CUtensorMap& tb, double* C, size_t ldc,
     counter = ring + (g_counter_next++ % NCOUNTERS);
     AB_CUDA_CHECK(cudaMemsetAsync(counter, 0, sizeof(int), current_stream()));
   }
-  dgemm_tma_kernel<AK, BK_><<<grid, THREADS, smem_req, current_stream()>>>(
+  dgemm_tma_kernel<AK, BK_, NI><<<grid, THREADS, smem_req, current_stream()>>>(
       ta, tb, C, ldc, M, N, K, alpha, beta, cmode, tiles_m, tiles_n, abort_flag, mask, counter);
   count_launch();
   AB_CUDA_CHECK(cudaGetLastError());
+}
+
+// 128 x 64 tiles when 128 x 128 tiles would not give every SM one (ATLB200_GEMM_BN=64|128 forces a width)
+int pick_ni(int M, int N) {
+  static const int forced = [] { const char* v = getenv("ATLB200_GEMM_BN"); return v ? atoi(v) : 0; }();
+  if (forced == 64) return 2;
+  if (forced == 128) return 4;
+  const long long t128 = (long long)((M + BM - 1) / BM) * ((N + 127) / 128);
+  return (t128 < gemm_cta_cap() && N > 64) ? 2 : 4;
 }
 
 }  // namespace
@@ -431,7 +454,7 @@ bool dgemm_tma_eligible(int M, int N, int K, const double* A, size_t lda, const 
   if (M <= 0 || N <= 0 || K <= 0) return false;
   if ((reinterpret_cast<uintptr_t>(A) & 15) || (reinterpret_cast<uintptr_t>(B) & 15)) return false;
   if ((lda & 1) || (ldb & 1)) return false;
-  if ((long long)((M + BM - 1) / BM) * ((N + BN - 1) / BN) > 0x7fffffffLL) return false;
+  if ((long long)((M + BM - 1) / BM) * ((N + 63) / 64) > 0x7fffffffLL) return false;
   return true;
 }
 
@@ -440,16 +463,18 @@ bool dgemm_tma(int ta, int tb, int M, int N, int K, double alpha, const double* 
   if (!dgemm_tma_eligible(M, N, K, A, lda, B, ldb)) return false;
   CUtensorMap mA, mB;
   bool ok;
+  const int ni = pick_ni(M, N);
   // op(A) is M x K.  ta: stored K x M (k contiguous, K-major) else stored M x K (m contiguous).
   ok = ta ? make_map(&mA, A, K, M, lda, BK, BM) : make_map(&mA, A, M, K, lda, 16, BK);
   if (!ok) return false;
   // op(B) is K x N.  !tb: stored K x N (K-major) else stored N x K (n contiguous).
-  ok = tb ? make_map(&mB, B, N, K, ldb, 16, BK) : make_map(&mB, B, K, N, ldb, BK, BN);
+  ok = tb ? make_map(&mB, B, N, K, ldb, 16, BK) : make_map(&mB, B, K, N, ldb, BK, 32 * ni);
   if (!ok) return false;
-  if (ta) { if (!tb) launch<true, true>(mA, mB, C, ldc, M, N, K, alpha, beta, cmode, abort_flag);
-            else     launch<true, false>(mA, mB, C, ldc, M, N, K, alpha, beta, cmode, abort_flag); }
-  else    { if (!tb) launch<false, true>(mA, mB, C, ldc, M, N, K, alpha, beta, cmode, abort_flag);
-            else     launch<false, false>(mA, mB, C, ldc, M, N, K, alpha, beta, cmode, abort_flag); }
+#define AB_GO(AK, BKM) do { if (ni == 2) launch<AK, BKM, 2>(mA, mB, C, ldc, M, N, K, alpha, beta, cmode, abort_flag); \
+                            else launch<AK, BKM, 4>(mA, mB, C, ldc, M, N, K, alpha, beta, cmode, abort_flag); } while (0)
+  if (ta) { if (!tb) AB_GO(true, true); else AB_GO(true, false); }
+  else    { if (!tb) AB_GO(false, true); else AB_GO(false, false); }
+#undef AB_GO
   return true;
 }
 

@@ -28,6 +28,7 @@
 #include <cfloat>
 #include <type_traits>
 #include <vector>
+#include <algorithm>
 
 namespace ab {
 
@@ -37,9 +38,9 @@ namespace { int env_int(const char* name, int dflt) { const char* v = getenv(nam
 // on which stream); the tables under profiles/ were made with it.  Off: no events, no cost.
 namespace {
 enum LuPhase { PH_LEAF, PH_SWAPTRSM, PH_PGEMM, PH_NEXT_SWAP, PH_NEXT_TRSM, PH_NEXT_GEMM, PH_REST_SWAP, PH_REST_TRSM, PH_REST_GEMM,
-               PH_LEFT_SWAP, PH_COUNT };
+               PH_LEFT_SWAP, PH_LLT_DIAG, PH_LLT_TRSM, PH_LLT_NEXT, PH_LLT_REST, PH_COUNT };
 const char* const kPhaseName[PH_COUNT] = {"leaf", "swap+trsm", "panel-gemm", "next:swap", "next:trsm", "next:gemm", "rest:swap",
-                                          "rest:trsm", "rest:gemm", "left:swap"};
+                                          "rest:trsm", "rest:gemm", "left:swap", "llt:diag", "llt:trsm", "llt:next", "llt:rest"};
 struct LuTracer {
   bool on = false;
   int step = 0;
@@ -91,9 +92,12 @@ thread_local LuTracer g_lutr;
 // __match_any / __any over the warp, and every thread gets pivot b by shuffle.
 template <typename T>
 __global__ void __launch_bounds__(64) laswp_kernel(int N, T* A, size_t lda, int K1, int K2,
-                                                    const int* piv, int inci) {
+                                                    const int* piv, int inci, int k1_step) {
   const int col = blockIdx.x * blockDim.x + threadIdx.x;
   const bool active = col < N;
+  // k1_step > 0 (a multiple of the CTA width): column block b = col / k1_step starts at pivot K1 + b*k1_step - the
+  // deferred "left of the panel" interchanges of a whole blocked factorisation in one launch
+  if (k1_step > 0) K1 += ((blockIdx.x * blockDim.x) / k1_step) * k1_step;
   const int lane = threadIdx.x & 31;
   T* a = A + (size_t)(active ? col : 0) * lda;
   if (inci >= 0) {
@@ -139,16 +143,18 @@ __global__ void __launch_bounds__(64) laswp_kernel(int N, T* A, size_t lda, int 
 }
 
 template <typename T>
-void laswp(int N, T* A, size_t lda, int K1, int K2, const int* d_piv, int inci) {
+static void laswp_blocks(int N, T* A, size_t lda, int K1, int K2, const int* d_piv, int inci, int k1_step) {
   if (N <= 0 || K2 <= K1) return;
 #ifdef ATLB200_DIAG
   if (diag::on_side() && (diag::pnop() & 2)) return;
 #endif
   const int threads = 64;
-  laswp_kernel<T><<<(N + threads - 1) / threads, threads, 0, current_stream()>>>(N, A, lda, K1, K2, d_piv, inci);
+  laswp_kernel<T><<<(N + threads - 1) / threads, threads, 0, current_stream()>>>(N, A, lda, K1, K2, d_piv, inci, k1_step);
   count_launch();
   AB_CUDA_CHECK(cudaGetLastError());
 }
+template <typename T>
+void laswp(int N, T* A, size_t lda, int K1, int K2, const int* d_piv, int inci) { laswp_blocks<T>(N, A, lda, K1, K2, d_piv, inci, 0); }
 
 // ------------------------------------------------------------------------------------- fused interchange + unit-lower solve
 // One step of the right-looking panel factorisation (see getrf_panel below): after the leaf has factored the
@@ -505,24 +511,126 @@ static void panel_launch(int M, int w, T* A, size_t lda, int* d_ipiv, int* d_inf
   count_launch();
 }
 
-// widest leaf panel whose M rows fit co-resident (narrower panels hold more rows per thread)
+// ---- panels taller than any co-resident variant (about 0.6-1.2 million rows on a B200): one column at a time, three
+// ordinary launches per column (partial arg-max / pick + interchange / scale + rank-1 update), no grid-wide barrier and
+// therefore no limit on M.  Same arithmetic as the leaves (iamax semantics through mag_key, reciprocal rule, the rank-1
+// update is applied even below a zero pivot, like ATL_Xgetf2, atlas-lp.base:5204-5379).
+constexpr int CW_PARTS = 512, CW_THREADS = 256;
+template <typename T> struct CwState { T piv; int nonzero, use_rcp; T rcp; };
+
+template <typename T>
+__global__ void __launch_bounds__(CW_THREADS) cw_part_kernel(int M, int j, const T* A, size_t lda, unsigned long long* pkey, int* prow) {
+  using S = ST<T>;
+  __shared__ unsigned long long sk[CW_THREADS];
+  __shared__ int sr[CW_THREADS];
+  unsigned long long key = 0; int row = 0x7fffffff;
+  const T* col = A + (size_t)j * lda;
+  for (long long i = j + (long long)blockIdx.x * CW_THREADS + threadIdx.x; i < M; i += (long long)CW_PARTS * CW_THREADS) {
+    const unsigned long long k = mag_key(S::abs1(col[i]));
+    if (k > key) { key = k; row = (int)i; }          // ascending i: strict > keeps the first
+  }
+  sk[threadIdx.x] = key; sr[threadIdx.x] = row;
+  __syncthreads();
+  for (int o = CW_THREADS / 2; o > 0; o >>= 1) {
+    if ((int)threadIdx.x < o) {
+      const unsigned long long ok = sk[threadIdx.x + o]; const int orow = sr[threadIdx.x + o];
+      if (ok > sk[threadIdx.x] || (ok == sk[threadIdx.x] && orow < sr[threadIdx.x])) { sk[threadIdx.x] = ok; sr[threadIdx.x] = orow; }
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) { pkey[blockIdx.x] = sk[0]; prow[blockIdx.x] = sr[0]; }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(CW_THREADS) cw_pick_kernel(int w, int j, T* A, size_t lda, const unsigned long long* pkey, const int* prow,
+                                                              int* ipiv, int* info, int piv_off, int info_off, CwState<T>* st) {
+  using S = ST<T>;
+  __shared__ unsigned long long sk[CW_THREADS];
+  __shared__ int sr[CW_THREADS];
+  unsigned long long key = 0; int row = 0x7fffffff;
+  for (int i = threadIdx.x; i < CW_PARTS; i += CW_THREADS) {
+    const unsigned long long k = pkey[i]; const int r = prow[i];
+    if (k > key || (k == key && r < row)) { key = k; row = r; }
+  }
+  sk[threadIdx.x] = key; sr[threadIdx.x] = row;
+  __syncthreads();
+  for (int o = CW_THREADS / 2; o > 0; o >>= 1) {
+    if ((int)threadIdx.x < o) {
+      const unsigned long long ok = sk[threadIdx.x + o]; const int orow = sr[threadIdx.x + o];
+      if (ok > sk[threadIdx.x] || (ok == sk[threadIdx.x] && orow < sr[threadIdx.x])) { sk[threadIdx.x] = ok; sr[threadIdx.x] = orow; }
+    }
+    __syncthreads();
+  }
+  const int p = (sr[0] == 0x7fffffff) ? j : sr[0];          // all-NaN column: iamax returns the first index
+  const T piv = A[(size_t)p + (size_t)j * lda];
+  const bool nonzero = !S::is_zero(piv);
+  __syncthreads();
+  if (nonzero && p != j)
+    for (int c = threadIdx.x; c < w; c += CW_THREADS) {
+      T* a = A + (size_t)c * lda;
+      const T t = a[j]; a[j] = a[p]; a[p] = t;
+    }
+  if (threadIdx.x == 0) {
+    ipiv[j] = p + piv_off;
+    if (!nonzero && *info == 0) *info = info_off + j + 1;
+    st->piv = piv; st->nonzero = nonzero ? 1 : 0;
+    st->use_rcp = (nonzero && S::abs1(piv) >= SafminC<T>::v()) ? 1 : 0;
+    st->rcp = nonzero ? c_recip<T>(piv) : S::zero();
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(CW_THREADS) cw_update_kernel(int M, int w, int j, T* A, size_t lda, const CwState<T>* st) {
+  using S = ST<T>;
+  const CwState<T> s = *st;
+  for (long long i = j + 1 + (long long)blockIdx.x * CW_THREADS + threadIdx.x; i < M; i += (long long)gridDim.x * CW_THREADS) {
+    T l = A[(size_t)i + (size_t)j * lda];
+    if (s.nonzero) { l = s.use_rcp ? S::mul(l, s.rcp) : c_div<T>(l, s.piv); A[(size_t)i + (size_t)j * lda] = l; }
+    for (int c = j + 1; c < w; c++) {
+      T* a = A + (size_t)c * lda;
+      a[i] = S::sub(a[i], S::mul(l, a[j]));
+    }
+  }
+}
+
+template <typename T>
+static void getf2_columnwise(int M, int w, T* A, size_t lda, int* d_ipiv, int* d_info, int piv_off, int info_off) {
+  char* ws = static_cast<char*>(workspace(CW_PARTS * 12 + sizeof(CwState<T>) + 256, 1));
+  unsigned long long* pkey = reinterpret_cast<unsigned long long*>(ws);
+  int* prow = reinterpret_cast<int*>(ws + CW_PARTS * 8);
+  CwState<T>* st = reinterpret_cast<CwState<T>*>(ws + CW_PARTS * 12 + 64 - (CW_PARTS * 12) % 64);
+  cudaStream_t s = current_stream();
+  const int MN = min(M, w);
+  const int ugrid = (int)std::min<long long>(4096, ((long long)M + CW_THREADS - 1) / CW_THREADS);
+  for (int j = 0; j < MN; j++) {
+    cw_part_kernel<T><<<CW_PARTS, CW_THREADS, 0, s>>>(M, j, A, lda, pkey, prow);
+    cw_pick_kernel<T><<<1, CW_THREADS, 0, s>>>(w, j, A, lda, pkey, prow, d_ipiv, d_info, piv_off, info_off, st);
+    if (j + 1 < M) cw_update_kernel<T><<<ugrid, CW_THREADS, 0, s>>>(M, w, j, A, lda, st);
+    count_launch(3);
+  }
+  AB_CUDA_CHECK(cudaGetLastError());
+}
+
+// widest leaf panel whose M rows fit co-resident (narrower panels hold more rows per thread); 0 = none fits
 template <typename T>
 static int panel_width_for(int M) {
   constexpr int W = PanelW<T>::W;
-  if (M <= panel_capacity<T, W, 1>()) return W;
-  if (M <= panel_capacity<T, W / 2, 2>()) return W / 2;
-  if (M <= panel_capacity<T, W / 4, 4>()) return W / 4;
-  fprintf(stderr, "atlas_b200: getrf with %d rows exceeds the co-resident panel capacity of this GPU\n", M);
-  abort();
+  static const long cap_override = env_int("ATLB200_LU_PANEL_CAP", 0);   // tests: pretend the device holds fewer rows
+  auto fits = [&](long cap) { return M <= (cap_override > 0 ? std::min(cap, cap_override) : cap); };
+  if (fits(panel_capacity<T, W, 1>())) return W;
+  if (fits(panel_capacity<T, W / 2, 2>())) return W / 2;
+  if (fits(panel_capacity<T, W / 4, 4>())) return W / 4;
+  return 0;
 }
 
 // factor an M x w panel, w <= leaf_w (the width panel_width_for() chose for the whole factorisation)
 template <typename T>
 static void getf2_panel(int M, int w, int leaf_w, T* A, size_t lda, int* d_ipiv, int* d_info, int piv_off, int info_off) {
   constexpr int W = PanelW<T>::W;
-  if (leaf_w == W) panel_launch<T, W, 1>(M, w, A, lda, d_ipiv, d_info, piv_off, info_off);
-  else if (leaf_w == W / 2) panel_launch<T, W / 2, 2>(M, w, A, lda, d_ipiv, d_info, piv_off, info_off);
-  else panel_launch<T, W / 4, 4>(M, w, A, lda, d_ipiv, d_info, piv_off, info_off);
+  if (leaf_w == W && panel_width_for<T>(M) == W) panel_launch<T, W, 1>(M, w, A, lda, d_ipiv, d_info, piv_off, info_off);
+  else if (leaf_w == W / 2 && panel_width_for<T>(M) >= W / 2) panel_launch<T, W / 2, 2>(M, w, A, lda, d_ipiv, d_info, piv_off, info_off);
+  else if (leaf_w == W / 4 && panel_width_for<T>(M) >= W / 4) panel_launch<T, W / 4, 4>(M, w, A, lda, d_ipiv, d_info, piv_off, info_off);
+  else getf2_columnwise<T>(M, w, A, lda, d_ipiv, d_info, piv_off, info_off);
 }
 
 // Leaf selection.  A panel of M rows is factored by the cluster kernel when one cluster can hold it
@@ -533,14 +641,18 @@ static int leaf_width_for(int M, bool* use_cluster) {
   constexpr int E = PanelW<T>::W;
   *use_cluster = true;
 #ifdef ATLB200_DIAG
-  if (diag::nocluster_on()) { *use_cluster = false; return panel_width_for<T>(M); }
+  if (diag::nocluster_on()) { *use_cluster = false; const int pw = panel_width_for<T>(M); return pw > 0 ? pw : E; }
 #endif
-  if (M <= cluster_capacity<T, E, 1>()) return E;
-  if (M <= cluster_capacity<T, E / 2, 2>()) return E / 2;
+  static const long cap_override = env_int("ATLB200_LU_PANEL_CAP", 0);   // tests: pretend the device holds fewer rows
+  if (!(cap_override > 0 && M > cap_override)) {
+    if (M <= cluster_capacity<T, E, 1>()) return E;
+    if (M <= cluster_capacity<T, E / 2, 2>()) return E / 2;
+  }
   // (an E/4-wide cluster leaf would hold 4x the rows, but measured slower than the global-barrier
   //  kernel at full width: too many tiny leaves and level-above launches)
   *use_cluster = false;
-  return panel_width_for<T>(M);
+  const int pw = panel_width_for<T>(M);
+  return pw > 0 ? pw : E;      // nothing co-resident fits: getf2_panel falls back to the column-at-a-time kernels
 }
 
 template <typename T>
@@ -654,17 +766,21 @@ static void getrf_rec(T* A0, size_t lda, int r0, int M, int N, int* d_ipiv, int*
 // unchanged (the same column-by-column search on the same updated values).
 namespace {
 struct SideStream {
-  cudaStream_t st = nullptr;
-  cudaEvent_t cols[2] = {nullptr, nullptr}, panel[2] = {nullptr, nullptr};
+  cudaStream_t st = nullptr, aux = nullptr;
+  cudaEvent_t cols[2] = {nullptr, nullptr}, panel[2] = {nullptr, nullptr}, have[2] = {nullptr, nullptr}, solved[2] = {nullptr, nullptr};
+
   int dev = -1;
   void ensure() {
     int d; AB_CUDA_CHECK(cudaGetDevice(&d));
     if (st && d == dev) return;
     dev = d;
     AB_CUDA_CHECK(cudaStreamCreateWithPriority(&st, cudaStreamNonBlocking, env_int("ATLB200_LU_SIDE_PRIO", -1)));   // panel work first
+    AB_CUDA_CHECK(cudaStreamCreateWithFlags(&aux, cudaStreamNonBlocking));
     for (int i = 0; i < 2; i++) {
       AB_CUDA_CHECK(cudaEventCreateWithFlags(&cols[i], cudaEventDisableTiming));
       AB_CUDA_CHECK(cudaEventCreateWithFlags(&panel[i], cudaEventDisableTiming));
+      AB_CUDA_CHECK(cudaEventCreateWithFlags(&have[i], cudaEventDisableTiming));
+      AB_CUDA_CHECK(cudaEventCreateWithFlags(&solved[i], cudaEventDisableTiming));
     }
   }
 };
@@ -799,7 +915,17 @@ static void getrf_lookahead(int M, int N, T* A, size_t lda, int* d_ipiv, int* d_
 #endif
   g_lutr.step = 0;
   getrf_rec<T>(A, lda, 0, M, min(NB, N), d_ipiv, d_info);          // panel 0 on the main stream
-  int nsteps = 0;
+  // The interchanges LEFT of a panel are needed by nobody during the factorisation: with ATLB200_LU_DEFER_LEFT (default)
+  // they are applied at the end, all column blocks in one launch, instead of one strided pass per block step.
+  const bool defer_left = env_int("ATLB200_LU_DEFER_LEFT", 0) != 0 && NB % 64 == 0;
+  // A third stream R takes the interchanges + U-block solve of the rest columns, so that they run beside the (narrow)
+  // update of the next panel's columns instead of delaying the trailing GEMM and the panel's cluster launches.
+  bool use_aux = env_int("ATLB200_LU_AUX", 1) != 0;
+#ifdef ATLB200_DIAG
+  if (dg.on) use_aux = false;
+#endif
+  cudaStream_t R = ss.aux;
+  int nsteps = 0, left_done = 0;       // left_done: columns [0, left_done) already carry all interchanges issued so far
   for (int k0 = 0, k = 0; k0 < MN; k0 += NB, k++) {
     nsteps = k + 1;
     g_lutr.step = k + 1;
@@ -807,6 +933,8 @@ static void getrf_lookahead(int M, int N, T* A, size_t lda, int* d_ipiv, int* d_
     const int c1 = k0 + w;                       // first column right of the panel
     const int nright = N - c1;
     const bool more = (c1 < MN);                 // is there a next panel to factor?
+    bool left_now = !defer_left;
+    bool r_synced = false;
     if (nright > 0) {
       const int w1 = more ? min(NB, MN - c1) : 0;   // (pivot columns only: what lies right of column MN is 'rest')
       // A panel too tall for one cluster is factored by the cooperative global-barrier kernel, whose
@@ -817,8 +945,26 @@ static void getrf_lookahead(int M, int N, T* A, size_t lda, int* d_ipiv, int* d_
       if (more && !cl) {
         lu_apply_panel<T>(A, lda, M, k0, w, c1, nright, d_ipiv);
         getrf_rec<T>(A, lda, c1, M - c1, w1, d_ipiv, d_info);
-        if (k0 > 0) laswp<T>(k0, A, lda, k0, k0 + w, d_ipiv, 1);
+        if (k0 > 0 && left_now) laswp<T>(k0, A, lda, k0, k0 + w, d_ipiv, 1);
         continue;
+      }
+      const int c0 = c1 + w1, nc = nright - w1;
+      T* Akk = A + (size_t)k0 + (size_t)k0 * lda;
+      const bool aux_step = use_aux && more && nc > 0;
+      if (aux_step) {
+        // R: interchanges and U block row of the rest columns, beside the next panel's update on U
+        r_synced = true;
+        AB_CUDA_CHECK(cudaEventRecord(ss.have[k & 1], U));
+        AB_CUDA_CHECK(cudaStreamWaitEvent(R, ss.have[k & 1], 0));
+        set_current_stream(R);
+        g_lutr.begin(PH_REST_SWAP);
+        laswp<T>(nc, A + (size_t)c0 * lda, lda, k0, k0 + w, d_ipiv, 1);
+        g_lutr.end();
+        g_lutr.begin(PH_REST_TRSM);
+        trsm<T>(Left, Lower, NoTrans, Unit, w, nc, S::one(), Akk, lda, A + (size_t)k0 + (size_t)c0 * lda, lda);
+        g_lutr.end();
+        AB_CUDA_CHECK(cudaEventRecord(ss.solved[k & 1], R));
+        set_current_stream(U);
       }
       if (more) {
         lu_apply_panel<T>(A, lda, M, k0, w, c1, w1, d_ipiv, PH_NEXT_SWAP);    // next panel's columns first
@@ -842,7 +988,6 @@ static void getrf_lookahead(int M, int N, T* A, size_t lda, int* d_ipiv, int* d_
       // shipped with the TRSM+GEMM held back until the panel had finished, because ~2 % of the runs changed
       // pivots with the full overlap; the cause was the DGEMM kernel's stage release - see mbar_release in
       // dgemm_tma.cu and DESIGN.md - and with it fixed the overlap is deterministic again.)
-      const int c0 = c1 + w1, nc = nright - w1;
       if (more) mark(U);
 #ifdef ATLB200_DIAG
       if (dg.on && more && nc > 0 && M - k0 - w > 0) {
@@ -851,7 +996,7 @@ static void getrf_lookahead(int M, int N, T* A, size_t lda, int* d_ipiv, int* d_
         T* U12 = A + (size_t)k0 + (size_t)c0 * lda;
         T* C22 = A + (size_t)(k0 + w) + (size_t)c0 * lda;
         laswp<T>(nc, A + (size_t)c0 * lda, lda, k0, k0 + w, d_ipiv, 1);
-        trsm<T>(Left, Lower, NoTrans, Unit, w, nc, S::one(), A + (size_t)k0 + (size_t)k0 * lda, lda, U12, lda);
+        trsm<T>(Left, Lower, NoTrans, Unit, w, nc, S::one(), Akk, lda, U12, lda);
         dg.before(k, rows, nc, w, A21, U12, C22, lda, U);
         if (diag::usync_on()) AB_CUDA_CHECK(cudaStreamSynchronize(U));
         if (diag::pnop() & 64) {
@@ -862,20 +1007,54 @@ static void getrf_lookahead(int M, int N, T* A, size_t lda, int* d_ipiv, int* d_
         dg.pending = true;
       } else
 #endif
-      lu_apply_panel<T>(A, lda, M, k0, w, c0, nc, d_ipiv);
+      if (aux_step) {
+        AB_CUDA_CHECK(cudaStreamWaitEvent(U, ss.solved[k & 1], 0));
+        if (M - k0 - w > 0) {
+          g_lutr.begin(PH_REST_GEMM);
+          gemm<T>(NoTrans, NoTrans, M - k0 - w, nc, w, S::from_real(-1), A + (size_t)(k0 + w) + (size_t)k0 * lda, lda,
+                  A + (size_t)k0 + (size_t)c0 * lda, lda, S::one(), A + (size_t)(k0 + w) + (size_t)c0 * lda, lda);
+          g_lutr.end();
+        }
+      } else
+        lu_apply_panel<T>(A, lda, M, k0, w, c0, nc, d_ipiv);
       if (more) mark(U);
       set_gemm_reserved(nullptr);
     }
-    if (k0 > 0) {                                                      // interchanges left of the panel
+    if (k0 > 0 && left_now) {                                          // interchanges left of the panel
+      // on R when it exists: nobody reads the left part during the factorisation, so they need not sit on U's path.
+      // They move rows of panel k-1's columns, which update k-1 (finished: R's `have` wait) was the last to read.
+      const bool on_r = use_aux && more && nright > 0;
+      if (on_r) {
+        if (!r_synced) {                              // R has not yet waited for U in this step
+          AB_CUDA_CHECK(cudaEventRecord(ss.have[k & 1], U));
+          AB_CUDA_CHECK(cudaStreamWaitEvent(R, ss.have[k & 1], 0));
+        }
+        set_current_stream(R);
+      }
       g_lutr.begin(PH_LEFT_SWAP);
       laswp<T>(k0, A, lda, k0, k0 + w, d_ipiv, 1);
       g_lutr.end();
+      if (on_r) set_current_stream(U);
+      left_done = k0;
     }
     if (more && nright > 0) AB_CUDA_CHECK(cudaStreamWaitEvent(U, ss.panel[k & 1], 0));
 #ifdef ATLB200_DIAG
     if (dg.pending) { set_gemm_reserved(nullptr); dg.after(U); }
 #endif
   }
+  if (use_aux) {          // R's last interchanges join the caller's stream
+    AB_CUDA_CHECK(cudaEventRecord(ss.solved[0], R));
+    AB_CUDA_CHECK(cudaStreamWaitEvent(U, ss.solved[0], 0));
+  }
+  if (defer_left && MN > NB) {
+    // column block b (columns [b*NB, (b+1)*NB)) takes the pivots of all later panels: rows (b+1)*NB .. MN-1
+    const int ncols = ((MN - 1) / NB) * NB;          // everything left of the last panel
+    g_lutr.step = nsteps;
+    g_lutr.begin(PH_LEFT_SWAP);
+    laswp_blocks<T>(ncols, A, lda, NB, MN, d_ipiv, 1, NB);
+    g_lutr.end();
+  }
+  (void)left_done;
 #ifdef ATLB200_DIAG
   dg.report();
 #endif
@@ -1034,44 +1213,62 @@ static void potrf_lookahead(int uplo, int N, T* A, size_t lda, int* d_info, int 
     if constexpr (S::cplx) herk<T>(uplo, lower ? NoTrans : ConjTrans, n, k, (R)-1, X, lda, (R)1, Cd, lda, d_info);
     else syrk<T>(uplo, lower ? NoTrans : TransT, n, k, S::from_real(-1), X, lda, S::one(), Cd, lda, d_info);
   };
-  auto factor_panel = [&](int k0, int w) {
-    T* Akk = A + (size_t)k0 + (size_t)k0 * lda;
-    potrf_rec<T>(uplo, w, Akk, lda, d_info, k0);
-    const int rest = N - k0 - w;
-    if (rest > 0) {
-      if (lower) trsm<T>(Right, Lower, tr, NonUnit, rest, w, S::one(), Akk, lda, Akk + w, lda, d_info);
-      else trsm<T>(Left, Upper, tr, NonUnit, w, rest, S::one(), Akk, lda, Akk + (size_t)w * lda, lda, d_info);
-    }
+  // The side stream P only factors the 512 x 512 diagonal block (a latency chain that needs a handful of SMs); the solve of
+  // the panel below / right of it runs on the main stream with the whole GPU - on P, beside the persistent rank-k update,
+  // it was starved to the reserved GPC (2.6 ms instead of 0.3 at N=16384; profiles/r02_potrf_phases.txt).
+  auto factor_diag = [&](int k0, int w) {
+    g_lutr.begin(PH_LLT_DIAG);
+    potrf_rec<T>(uplo, w, A + (size_t)k0 + (size_t)k0 * lda, lda, d_info, k0);
+    g_lutr.end();
   };
-  factor_panel(0, min(NB, N));
+  auto solve_panel = [&](int k0, int w) {
+    T* Akk = A + (size_t)k0 + (size_t)k0 * lda;
+    const int rest = N - k0 - w;
+    if (rest <= 0) return;
+    g_lutr.begin(PH_LLT_TRSM);
+    if (lower) trsm<T>(Right, Lower, tr, NonUnit, rest, w, S::one(), Akk, lda, Akk + w, lda, d_info);
+    else trsm<T>(Left, Upper, tr, NonUnit, w, rest, S::one(), Akk, lda, Akk + (size_t)w * lda, lda, d_info);
+    g_lutr.end();
+  };
+  const int trace = env_int("ATLB200_LU_TRACE", 0);
+  g_lutr.on = trace >= 2;
+  g_lutr.step = 0;
+  factor_diag(0, min(NB, N));
+  int nsteps = 0;
   for (int k0 = 0, k = 0; k0 < N; k0 += NB, k++) {
     const int w = min(NB, N - k0), c1 = k0 + w, rest = N - c1;
     if (rest <= 0) break;
+    nsteps = k + 1;
+    g_lutr.step = k + 1;
     const int w1 = min(NB, rest);
+    solve_panel(k0, w);                            // diagonal block k is complete on U here
     // factored panel below / right of the diagonal block
     const T* X = lower ? A + (size_t)c1 + (size_t)k0 * lda : A + (size_t)k0 + (size_t)c1 * lda;
     T* Ann = A + (size_t)c1 + (size_t)c1 * lda;
-    // ---- next panel first
+    // ---- next diagonal block first: only IT is needed by the chain; the rest of the next panel's column joins the rest update
+    g_lutr.begin(PH_LLT_NEXT);
     rank_k(w1, w, X, Ann);
-    if (rest > w1) {
-      if (lower) gemm<T>(NoTrans, tr, rest - w1, w1, w, S::from_real(-1), X + w1, lda, X, lda, S::one(), Ann + w1, lda, d_info);
-      else gemm<T>(tr, NoTrans, w1, rest - w1, w, S::from_real(-1), X, lda, X + (size_t)w1 * lda, lda, S::one(), Ann + (size_t)w1 * lda, lda, d_info);
-    }
+    g_lutr.end();
     AB_CUDA_CHECK(cudaEventRecord(ss.cols[k & 1], U));
     AB_CUDA_CHECK(cudaStreamWaitEvent(P, ss.cols[k & 1], 0));
     set_current_stream(P);
-    factor_panel(c1, w1);
+    factor_diag(c1, w1);
     AB_CUDA_CHECK(cudaEventRecord(ss.panel[k & 1], P));
     set_current_stream(U);
     // ---- the rest of the trailing triangle beside it
     if (rest > w1) {
       set_gemm_reserved(reserved);
+      g_lutr.begin(PH_LLT_REST);
+      if (lower) gemm<T>(NoTrans, tr, rest - w1, w1, w, S::from_real(-1), X + w1, lda, X, lda, S::one(), Ann + w1, lda, d_info);
+      else gemm<T>(tr, NoTrans, w1, rest - w1, w, S::from_real(-1), X, lda, X + (size_t)w1 * lda, lda, S::one(), Ann + (size_t)w1 * lda, lda, d_info);
       const T* X2 = lower ? X + w1 : X + (size_t)w1 * lda;
       rank_k(rest - w1, w, X2, Ann + (size_t)w1 + (size_t)w1 * lda);
+      g_lutr.end();
       set_gemm_reserved(nullptr);
     }
     AB_CUDA_CHECK(cudaStreamWaitEvent(U, ss.panel[k & 1], 0));
   }
+  if (trace >= 2) { g_lutr.report(nsteps); g_lutr.on = false; }
 }
 
 template <typename T>

@@ -105,6 +105,16 @@ class CudaOps:
     def close(self):
         self.L.atlb200_set_async(0)
 
+    def side_stream(self):
+        """a high-priority CUDA stream for the panel chain of the rank that owns the next panel (pgetrf / ppotrf)"""
+        if getattr(self, "_side", None) is None:
+            self._side = torch.cuda.Stream(priority=-1)
+        return self._side
+
+    def use_stream(self, stream):
+        """make `stream` (a torch.cuda.Stream, or None for the default stream) the library's launch stream of this thread"""
+        self.L.atlb200_set_stream(C.c_void_p(stream.cuda_stream if stream is not None else 0))
+
     def reserve(self, n):
         """n > 0: large GEMMs leave n SMs free and share their tiles dynamically; n < 0: dynamic sharing
         only; 0: off.  A persistent update GEMM otherwise holds every SM until it ends: on the panel
@@ -159,6 +169,25 @@ def pgemm(ops, M, N_local, K, alpha, A, lda, B_loc, ldb, beta, C_loc, ldc):
     """This rank's column slab of C <- alpha*A*B + beta*C.  No collective: the output is partitioned
     by columns and K is never split (reference decomposition ATL_thrdecompMM, atlas-thr.base:5197)."""
     ops.gemm(CblasNoTrans, CblasNoTrans, M, N_local, K, alpha, A.data_ptr(), lda, B_loc.data_ptr(), ldb, beta, C_loc.data_ptr(), ldc)
+
+
+def pgemm_host(pre, M, N_local, K, alpha, hA, lda, hB_loc, ldb, beta, hC_loc, ldc, dA, rank, world, group=None):
+    """End-to-end GEMM from HOST memory on `world` GPUs: C slab <- alpha*A*B slab + beta*C slab (NoTrans/NoTrans).
+    Every rank sees the whole of A in (pinned) host memory; rank r uploads only columns [r*K/world, (r+1)*K/world) of A,
+    the ranks all-gather the slabs over NVLink (one ncclAllGather, 2 GiB at N=16384) into dA, and the library's
+    column-panel pipeline (H2D of B/C panels, GEMM, D2H) runs with A already on the device.  PCIe traffic per rank drops
+    from 8*(M*K + 2*K*N_local) to 8*(M*K/world + 2*K*N_local) bytes.
+    hA: torch CPU tensor (K, lda) = column-major M x K; dA: device tensor (K, lda) scratch; hB_loc/hC_loc: host slabs."""
+    from . import cblas_gemm
+    assert K % world == 0
+    ks = K // world
+    dev = dA.device
+    slab = dA[rank * ks:(rank + 1) * ks]
+    slab.copy_(hA[rank * ks:(rank + 1) * ks], non_blocking=True)          # H2D of this rank's share of A
+    if world > 1:
+        dist.all_gather_into_tensor(dA, slab, group=group)              # NVLink; in place: slab is rank's chunk of dA
+    cblas_gemm(pre, CblasColMajor, CblasNoTrans, CblasNoTrans, M, N_local, K, alpha, dA.data_ptr(), lda, hB_loc.data_ptr(), ldb, beta,
+               hC_loc.data_ptr(), ldc)
 
 
 def psyrk(ops, uplo, N, K, c0, c1, alpha, A, lda, beta, C_loc, ldc):
@@ -255,6 +284,7 @@ def pgetrf(pre, M, lay, A_loc, ld, ops, group=None, lookahead=True):
             e = torch.cuda.Event(enable_timing=True); e.record(); marks.append((k, tag, e))
 
     overlap = lookahead and lay.q > 1 and hasattr(ops, "reserve")
+    side = ops.side_stream() if (overlap and hasattr(ops, "side_stream") and os.environ.get("ATLB200_DIST_SIDE", "1") != "0") else None
     if overlap:
         ops.reserve(-1)     # every trailing update shares its tiles dynamically (see CudaOps.reserve)
     buf, work = post(0)
@@ -274,10 +304,19 @@ def pgetrf(pre, M, lay, A_loc, ld, ops, group=None, lookahead=True):
             w1 = lay.width(k + 1)
             update(k, P, piv, t0, t0 + w1)          # bring the next panel up to date first ...
             mark(k, "next_cols")
-            nbuf, nwork = post(k + 1)               # ... factor it and start its broadcast ...
+            if side is not None:
+                # ... factor it and start its broadcast on a second, high-priority stream, so that this rank's own trailing
+                # update runs BESIDE its panel (round 1 ran them in line: the owner's panel + update bounded every step)
+                side.wait_stream(torch.cuda.current_stream())
+                ops.use_stream(side)
+                with torch.cuda.stream(side):
+                    nbuf, nwork = post(k + 1)
+                ops.use_stream(None)
+            else:
+                nbuf, nwork = post(k + 1)           # ... factor it and start its broadcast ...
             mark(k, "factored")
             if overlap:
-                ops.reserve(8)                      # (room for the broadcast's kernels, starting now, beside the GEMM)
+                ops.reserve(16 if side is not None else 8)   # room for the panel's cluster / the broadcast's kernels beside the GEMM
             update(k, P, piv, t0 + w1, lay.ncols_local)   # ... which overlaps the rest of the update
             if overlap:
                 ops.reserve(-1)
@@ -350,6 +389,7 @@ def ppotrf(pre, lay, A_loc, ld, ops, group=None, lookahead=True):
                      1.0, addr(A_loc, j0 + wj, lj, ld), ld)
 
     overlap = lookahead and lay.q > 1 and hasattr(ops, "reserve")
+    side = ops.side_stream() if (overlap and hasattr(ops, "side_stream") and os.environ.get("ATLB200_DIST_SIDE", "1") != "0") else None
     if overlap:
         ops.reserve(8)      # as in pgetrf: the next panel's broadcast must be able to run beside the updates
     buf, work = post(0)
@@ -364,7 +404,14 @@ def ppotrf(pre, lay, A_loc, ld, ops, group=None, lookahead=True):
         nxt = k + 1 < lay.nblocks
         if nxt and lookahead and rank == lay.owner(k + 1):
             update_block(k, P, Mk, k + 1)
-            nbuf, nwork = post(k + 1)
+            if side is not None:                    # the owner's panel + broadcast beside its own trailing update
+                side.wait_stream(torch.cuda.current_stream())
+                ops.use_stream(side)
+                with torch.cuda.stream(side):
+                    nbuf, nwork = post(k + 1)
+                ops.use_stream(None)
+            else:
+                nbuf, nwork = post(k + 1)
             for j in trailing:
                 if j != k + 1:
                     update_block(k, P, Mk, j)
