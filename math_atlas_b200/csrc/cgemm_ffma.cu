@@ -20,6 +20,7 @@ struct CParams {
   int cmode, herk;
   int a_vec, b_vec;   // 16-byte aligned base + even leading dimension
   const int* abort_flag;
+  const int* run_flag;     // if non-null the kernel runs only when *run_flag != 0 (tensor-core path declined on the device)
 };
 
 // 64 x 8 complex = 2 per thread.  MN-contiguous: element (r,k) at P[r + k*ld], 2 consecutive r per thread.
@@ -56,6 +57,7 @@ __device__ __forceinline__ void store_k(float2 (*S)[BM + PAD], const float2 (&v)
 
 __global__ void __launch_bounds__(THREADS, 2) cgemm_ffma_kernel(const CParams p) {
   if (p.abort_flag && *p.abort_flag) return;
+  if (p.run_flag && !*p.run_flag) return;
   __shared__ __align__(16) float2 As[2][BK][BM + PAD];
   __shared__ __align__(16) float2 Bs[2][BK][BN + PAD];
   // grouped rasterisation: GROUP_M tile rows share their B panel in L2 (same map as dgemm_tma.cu)
@@ -139,13 +141,13 @@ __global__ void __launch_bounds__(THREADS, 2) cgemm_ffma_kernel(const CParams p)
 }  // namespace
 
 bool cgemm_ffma(int ta, int ca, int tb, int cb, int M, int N, int K, float2 alpha, const float2* A, size_t lda, const float2* B,
-                size_t ldb, float2 beta, float2* C, size_t ldc, int cmode, int herk, const int* abort_flag) {
+                size_t ldb, float2 beta, float2* C, size_t ldc, int cmode, int herk, const int* abort_flag, const int* run_flag) {
   if (M <= 0 || N <= 0 || K <= 0) return false;
   const int gx = (M + BM - 1) / BM, gy = (N + BN - 1) / BN;
   if ((long long)gx * gy > 0x7fffffffLL) return false;
   CParams p{M, N, K, A, lda, ta, ca, B, ldb, tb, cb, alpha, beta, C, ldc, cmode, herk,
             (int)(((reinterpret_cast<uintptr_t>(A) & 15) == 0) && (lda % 2 == 0)),
-            (int)(((reinterpret_cast<uintptr_t>(B) & 15) == 0) && (ldb % 2 == 0)), abort_flag};
+            (int)(((reinterpret_cast<uintptr_t>(B) & 15) == 0) && (ldb % 2 == 0)), abort_flag, run_flag};
   cgemm_ffma_kernel<<<gx * gy, THREADS, 0, current_stream()>>>(p);
   count_launch();
   AB_CUDA_CHECK(cudaGetLastError());

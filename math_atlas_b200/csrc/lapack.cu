@@ -733,7 +733,9 @@ static void getrf_rec(T* A0, size_t lda, int r0, int M, int N, int* d_ipiv, int*
   const int leaf_w = leaf_width_for<T>(M, &use_cluster);
   // nodes up to ATLB200_LU_PW columns are factored right-looking by getrf_panel (3 launches per leaf width);
   // above that the reference's recursion keeps the updates as large-K GEMMs
-  static const int pw = env_int("ATLB200_LU_PW", 512);
+  static const int pw_short = env_int("ATLB200_LU_PW", 512);
+  static const int pw_tall = env_int("ATLB200_LU_PW_TALL", pw_short);   // panels whose leaves are half width (more rows than one full-width cluster holds)
+  const int pw = (leaf_w < PanelW<T>::W) ? pw_tall : pw_short;
   if (N <= max(leaf_w, pw)) {
     getrf_panel<T>(A0, lda, r0, M, N, d_ipiv, d_info);
     return;
@@ -934,7 +936,6 @@ static void getrf_lookahead(int M, int N, T* A, size_t lda, int* d_ipiv, int* d_
     const int nright = N - c1;
     const bool more = (c1 < MN);                 // is there a next panel to factor?
     bool left_now = !defer_left;
-    bool r_synced = false;
     if (nright > 0) {
       const int w1 = more ? min(NB, MN - c1) : 0;   // (pivot columns only: what lies right of column MN is 'rest')
       // A panel too tall for one cluster is factored by the cooperative global-barrier kernel, whose
@@ -953,7 +954,6 @@ static void getrf_lookahead(int M, int N, T* A, size_t lda, int* d_ipiv, int* d_
       const bool aux_step = use_aux && more && nc > 0;
       if (aux_step) {
         // R: interchanges and U block row of the rest columns, beside the next panel's update on U
-        r_synced = true;
         AB_CUDA_CHECK(cudaEventRecord(ss.have[k & 1], U));
         AB_CUDA_CHECK(cudaStreamWaitEvent(R, ss.have[k & 1], 0));
         set_current_stream(R);
@@ -1021,20 +1021,11 @@ static void getrf_lookahead(int M, int N, T* A, size_t lda, int* d_ipiv, int* d_
       set_gemm_reserved(nullptr);
     }
     if (k0 > 0 && left_now) {                                          // interchanges left of the panel
-      // on R when it exists: nobody reads the left part during the factorisation, so they need not sit on U's path.
-      // They move rows of panel k-1's columns, which update k-1 (finished: R's `have` wait) was the last to read.
-      const bool on_r = use_aux && more && nright > 0;
-      if (on_r) {
-        if (!r_synced) {                              // R has not yet waited for U in this step
-          AB_CUDA_CHECK(cudaEventRecord(ss.have[k & 1], U));
-          AB_CUDA_CHECK(cudaStreamWaitEvent(R, ss.have[k & 1], 0));
-        }
-        set_current_stream(R);
-      }
+      // (on U, after the trailing GEMM: on the aux stream they ran beside that GEMM, and 64-thread laswp CTAs that share
+      //  an SM with a DGEMM CTA slow it down - rest:gemm 90 -> 117 ms in total at N=16384, profiles/r02_lu_phases.txt)
       g_lutr.begin(PH_LEFT_SWAP);
       laswp<T>(k0, A, lda, k0, k0 + w, d_ipiv, 1);
       g_lutr.end();
-      if (on_r) set_current_stream(U);
       left_done = k0;
     }
     if (more && nright > 0) AB_CUDA_CHECK(cudaStreamWaitEvent(U, ss.panel[k & 1], 0));
@@ -1206,7 +1197,20 @@ static void potrf_lookahead(int uplo, int N, T* A, size_t lda, int* d_info, int 
   SideStream& ss = g_side;
   ss.ensure();
   cudaStream_t U = current_stream(), P = ss.st;
-  const unsigned long long* reserved = env_int("ATLB200_LU_RESERVE", 1) ? cluster_reserved_mask() : nullptr;
+  // the side stream only runs the small kernels of a 512 x 512 diagonal block (no thread-block cluster): a few SMs kept
+  // free of update CTAs are enough (ATLB200_LLT_RESERVE, default 8; the LU reserves a whole GPC for its cluster leaf)
+  unsigned long long llt_mask[4] = {0, 0, 0, 0};
+  const unsigned long long* reserved = nullptr;
+  {
+    const int want = env_int("ATLB200_LLT_RESERVE", 8);
+    const unsigned long long* full = (want > 0 && env_int("ATLB200_LU_RESERVE", 1)) ? cluster_reserved_mask() : nullptr;
+    if (full) {
+      int taken = 0;
+      for (int i = 0; i < 256 && taken < want; i++)
+        if (full[i >> 6] >> (i & 63) & 1ull) { llt_mask[i >> 6] |= 1ull << (i & 63); taken++; }
+      reserved = llt_mask;
+    }
+  }
   const int tr = S::cplx ? ConjTrans : TransT;
   const bool lower = (uplo == Lower);
   auto rank_k = [&](int n, int k, const T* X, T* Cd) {      // Cd(tri) -= X X^H (Lower: X is n x k) or X^H X (Upper: X is k x n)

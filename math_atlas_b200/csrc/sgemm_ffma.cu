@@ -22,6 +22,7 @@ struct SParams {
   int cmode;
   int a_vec, b_vec, c_vec;   // 16-byte aligned base + leading dimension multiple of 4
   const int* abort_flag;
+  const int* run_flag;     // if non-null the kernel runs only when *run_flag != 0 (tensor-core path declined on the device)
 };
 
 // ---- tile loaders: 128 x 8 floats = 4 per thread, fetched into registers ----
@@ -58,6 +59,7 @@ __device__ __forceinline__ void store_k(float (*S)[BM + PAD], const float (&v)[4
 
 __global__ void __launch_bounds__(THREADS, 2) sgemm_ffma_kernel(const SParams p) {
   if (p.abort_flag && *p.abort_flag) return;
+  if (p.run_flag && !*p.run_flag) return;
   __shared__ __align__(16) float As[2][BK][BM + PAD];
   __shared__ __align__(16) float Bs[2][BK][BN + PAD];
   // grouped rasterisation: GROUP_M tile rows share their B panel in L2 (same map as dgemm_tma.cu)
@@ -145,14 +147,14 @@ __global__ void __launch_bounds__(THREADS, 2) sgemm_ffma_kernel(const SParams p)
 }  // namespace
 
 bool sgemm_ffma(int ta, int tb, int M, int N, int K, float alpha, const float* A, size_t lda, const float* B, size_t ldb, float beta,
-                float* C, size_t ldc, int cmode, const int* abort_flag) {
+                float* C, size_t ldc, int cmode, const int* abort_flag, const int* run_flag) {
   if (M <= 0 || N <= 0 || K <= 0) return false;
   const int gx = (M + BM - 1) / BM, gy = (N + BN - 1) / BN;
   if ((long long)gx * gy > 0x7fffffffLL) return false;
   SParams p{M, N, K, A, lda, ta, B, ldb, tb, alpha, beta, C, ldc, cmode,
             (int)(((reinterpret_cast<uintptr_t>(A) & 15) == 0) && (lda % 4 == 0)),
             (int)(((reinterpret_cast<uintptr_t>(B) & 15) == 0) && (ldb % 4 == 0)),
-            (int)(((reinterpret_cast<uintptr_t>(C) & 15) == 0) && (ldc % 4 == 0)), abort_flag};
+            (int)(((reinterpret_cast<uintptr_t>(C) & 15) == 0) && (ldc % 4 == 0)), abort_flag, run_flag};
   sgemm_ffma_kernel<<<gx * gy, THREADS, 0, current_stream()>>>(p);
   count_launch();
   AB_CUDA_CHECK(cudaGetLastError());

@@ -97,7 +97,27 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
 // Access-major panels: P_hi/P_lo[((k/32) * Rp + r) * 32 + k%32] for r < Rp, k < Kp (zero padded), so the 128 x 32
 // (256 x 32) block one TMA instruction fetches is one contiguous 16 (32) KB piece of memory - ATLAS's block-major
 // copy format.  op(X)(r,k) = X[r + k*ld] (kcontig=0) or X[k + r*ld] (kcontig=1)
-__global__ void __launch_bounds__(256) split_pack_kernel(int R, int K, int Rp, int Kp, const float* X, size_t ld, int kcontig,
+// a = hi + lo with hi, lo representable in TF32.  hi = rna(a); for finite |a| so close to FLT_MAX that rounding to nearest
+// overflows, hi is the truncation instead (the difference stays exact); for a = +-Inf or NaN, hi = a and lo = 0, so that
+// products come out Inf / NaN exactly where FP32 arithmetic gives them (`a - Inf` used to put NaN into lo).
+// Operands that are Inf or NaN cannot go through the split at all (Inf * b_lo is NaN or -Inf where FP32 gives +Inf): the
+// copy kernels raise a device flag, the tensor-core kernel then leaves at once and the exact FFMA kernel queued behind it
+// - which otherwise leaves at once - computes the product instead.  No host round trip: the LU / Cholesky drivers issue
+// these GEMMs asynchronously.
+__device__ __forceinline__ void tf32_split(float a, float& hi, float& lo, int* nonfinite) {
+  if (!isfinite(a)) *nonfinite = 1;
+  uint32_t hb, lb;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hb) : "f"(a));
+  hi = __uint_as_float(hb);
+  if (!isfinite(hi)) {
+    if (isfinite(a)) hi = __uint_as_float(__float_as_uint(a) & 0xffffe000u);
+    else { hi = a; lo = 0.f; return; }
+  }
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(lb) : "f"(a - hi));
+  lo = __uint_as_float(lb);
+}
+
+__global__ void __launch_bounds__(256) split_pack_kernel(int* nonfinite, int R, int K, int Rp, int Kp, const float* X, size_t ld, int kcontig,
                                                          float* Ph, float* Pl) {
   __shared__ float t[32][33];
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;     // 32 x 8
@@ -121,31 +141,27 @@ __global__ void __launch_bounds__(256) split_pack_kernel(int R, int K, int Rp, i
     const int r = r0 + ty + 8 * i, k = k0 + tx;
     if (r < Rp && k < Kp) {
       const float a = t[ty + 8 * i][tx];
-      uint32_t hb, lb;
-      asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hb) : "f"(a));
-      const float hi = __uint_as_float(hb);
-      asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(lb) : "f"(a - hi));
+      float hi, lo;
+      tf32_split(a, hi, lo, nonfinite);
       const size_t o = ((size_t)blockIdx.x * Rp + r) * 32 + tx;      // blockIdx.x = k / 32
       Ph[o] = hi;
-      Pl[o] = __uint_as_float(lb);
+      Pl[o] = lo;
     }
   }
 }
 
-__device__ __forceinline__ void split_store(float* Ph, float* Pl, size_t o, float a) {
-  uint32_t hb, lb;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hb) : "f"(a));
-  const float hi = __uint_as_float(hb);
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(lb) : "f"(a - hi));
+__device__ __forceinline__ void split_store(float* Ph, float* Pl, size_t o, float a, int* nonfinite) {
+  float hi, lo;
+  tf32_split(a, hi, lo, nonfinite);
   Ph[o] = hi;
-  Pl[o] = __uint_as_float(lb);
+  Pl[o] = lo;
 }
 // complex cm2am.  X is float2; op(X)(r,k) = X[r + k*ld] (kcontig=0) or X[k + r*ld] (kcontig=1), conjugated if cj.
 // KBh = Kp/32 k blocks hold the first half of the doubled K, the next KBh the second half.
 //   isB = 0: packed row r:  [ re(r,k) | im(r,k) ]                                   (Rp rows)
 //   isB = 1: complex column n -> packed rows 256*(n/128) + n%128 ("re" row): [ re(k,n) | -im(k,n) ]
 //                                        and 256*(n/128) + 128 + n%128 ("im" row): [ im(k,n) |  re(k,n) ]
-__global__ void __launch_bounds__(256) split_pack_cplx_kernel(int R, int K, int Rp, int Kp, const float2* X, size_t ld,
+__global__ void __launch_bounds__(256) split_pack_cplx_kernel(int* nonfinite, int R, int K, int Rp, int Kp, const float2* X, size_t ld,
                                                               int kcontig, int cj, int isB, float* Ph, float* Pl) {
   __shared__ float2 t[32][33];
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
@@ -173,14 +189,14 @@ __global__ void __launch_bounds__(256) split_pack_cplx_kernel(int R, int K, int 
     if (cj) a.y = -a.y;
     const size_t kb1 = blockIdx.x, kb2 = blockIdx.x + KBh;
     if (!isB) {
-      split_store(Ph, Pl, (kb1 * prow + r) * 32 + tx, a.x);
-      split_store(Ph, Pl, (kb2 * prow + r) * 32 + tx, a.y);
+      split_store(Ph, Pl, (kb1 * prow + r) * 32 + tx, a.x, nonfinite);
+      split_store(Ph, Pl, (kb2 * prow + r) * 32 + tx, a.y, nonfinite);
     } else {
       const size_t rr = 256 * (size_t)(r / 128) + (r % 128), ri = rr + 128;
-      split_store(Ph, Pl, (kb1 * prow + rr) * 32 + tx, a.x);
-      split_store(Ph, Pl, (kb2 * prow + rr) * 32 + tx, -a.y);
-      split_store(Ph, Pl, (kb1 * prow + ri) * 32 + tx, a.y);
-      split_store(Ph, Pl, (kb2 * prow + ri) * 32 + tx, a.x);
+      split_store(Ph, Pl, (kb1 * prow + rr) * 32 + tx, a.x, nonfinite);
+      split_store(Ph, Pl, (kb2 * prow + rr) * 32 + tx, -a.y, nonfinite);
+      split_store(Ph, Pl, (kb1 * prow + ri) * 32 + tx, a.y, nonfinite);
+      split_store(Ph, Pl, (kb2 * prow + ri) * 32 + tx, a.x, nonfinite);
     }
   }
 }
@@ -248,9 +264,10 @@ template <bool CPLX>
 __global__ void __launch_bounds__(THREADS, 1)
 sgemm_tc_kernel(const __grid_constant__ CUtensorMap mAh, const __grid_constant__ CUtensorMap mAl,
                 const __grid_constant__ CUtensorMap mBh, const __grid_constant__ CUtensorMap mBl, float* C, size_t ldc, int M,
-                int N, int KB, float alpha, float beta, int cmode, int tiles_m, int tiles_n, const int* abort_flag,
+                int N, int KB, float alpha, float beta, int cmode, int tiles_m, int tiles_n, const int* abort_flag, const int* skip,
                 float alpha_im, float beta_im, int herk) {
   if (abort_flag && *abort_flag) return;
+  if (skip && *skip) return;                            // non-finite operands: the FFMA kernel behind this one takes over
   constexpr int TN = CPLX ? BN / 2 : BN;               // output columns per tile (complex: 128)
   // grouped rasterisation (same map as dgemm_tma.cu)
   const int in_group = GROUP_M * tiles_n;
@@ -364,9 +381,10 @@ template <bool CPLX>
 __global__ void __launch_bounds__(THREADS, 1)
 sgemm_tc2_kernel(const __grid_constant__ CUtensorMap mAh, const __grid_constant__ CUtensorMap mAl,
                  const __grid_constant__ CUtensorMap mBh, const __grid_constant__ CUtensorMap mBl, float* C, size_t ldc, int M,
-                 int N, int KB, float alpha, float beta, int cmode, int tiles_m, int tiles_n, const int* abort_flag,
+                 int N, int KB, float alpha, float beta, int cmode, int tiles_m, int tiles_n, const int* abort_flag, const int* skip,
                  float alpha_im, float beta_im, int herk) {
   if (abort_flag && *abort_flag) return;                 // (uniform over the grid: both CTAs of a pair leave)
+  if (skip && *skip) return;                             // non-finite operands: the FFMA kernel behind this one takes over
   constexpr int TN = CPLX ? BN / 2 : BN;
   uint32_t rank;
   asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(rank));
@@ -485,7 +503,7 @@ static int tc_variant() {
 }
 template <bool CPLX>
 static void launch_tc(const CUtensorMap& mAh, const CUtensorMap& mAl, const CUtensorMap& mBh, const CUtensorMap& mBl, float* C, size_t ldc, int M,
-                      int N, int KB, float alpha, float beta, int cmode, int tiles_m128, int tiles_n, const int* abort_flag, float alpha_im,
+                      int N, int KB, float alpha, float beta, int cmode, int tiles_m128, int tiles_n, const int* abort_flag, const int* skip, float alpha_im,
                       float beta_im, int herk) {
   if (tc_variant() == 2) {
     static PerDeviceOnce attr_once;
@@ -499,12 +517,12 @@ static void launch_tc(const CUtensorMap& mAh, const CUtensorMap& mAl, const CUte
     at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
     cfg.attrs = at; cfg.numAttrs = 1;
     AB_CUDA_CHECK(cudaLaunchKernelEx(&cfg, sgemm_tc2_kernel<CPLX>, mAh, mAl, mBh, mBl, C, ldc, M, N, KB, alpha, beta, cmode, tiles_m256, tiles_n,
-                                     abort_flag, alpha_im, beta_im, herk));
+                                     abort_flag, skip, alpha_im, beta_im, herk));
   } else {
     static PerDeviceOnce attr_once;
     attr_once([] { AB_CUDA_CHECK(cudaFuncSetAttribute(sgemm_tc_kernel<CPLX>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES)); });
     sgemm_tc_kernel<CPLX><<<(unsigned)tiles_m128 * (unsigned)tiles_n, THREADS, SMEM_BYTES, current_stream()>>>(
-        mAh, mAl, mBh, mBl, C, ldc, M, N, KB, alpha, beta, cmode, tiles_m128, tiles_n, abort_flag, alpha_im, beta_im, herk);
+        mAh, mAl, mBh, mBl, C, ldc, M, N, KB, alpha, beta, cmode, tiles_m128, tiles_n, abort_flag, skip, alpha_im, beta_im, herk);
   }
   count_launch();
   AB_CUDA_CHECK(cudaGetLastError());
@@ -545,12 +563,14 @@ bool sgemm_tc(int ta, int tb, int M, int N, int K, float alpha, const float* A, 
   // stream-ordered pool allocation: the look-ahead factorisations issue GEMMs from two streams
   float* ws = nullptr;
   keep_pool_cached();
-  AB_CUDA_CHECK(cudaMallocAsync(&ws, bytes, current_stream()));
+  AB_CUDA_CHECK(cudaMallocAsync(&ws, bytes + 64, current_stream()));
   float *Ah = ws, *Al = Ah + Mp * Kp, *Bh = Al + Mp * Kp, *Bl = Bh + Np * Kp;
+  int* nf = reinterpret_cast<int*>(reinterpret_cast<char*>(ws) + bytes);      // "an operand is Inf/NaN" (see tf32_split)
+  AB_CUDA_CHECK(cudaMemsetAsync(nf, 0, sizeof(int), current_stream()));
   // cm2am: op(A)(m,k) = A[m + k*lda] (NoTrans) or A[k + m*lda] (Trans: K contiguous); op(B)(k,n): rows of the packed
   // panel are n, so B NoTrans (B[k + n*ldb]) is the K-contiguous case
-  split_pack_kernel<<<dim3((unsigned)(Kp / 32), (unsigned)(Mp / 32)), 256, 0, current_stream()>>>(M, K, (int)Mp, (int)Kp, A, lda, ta ? 1 : 0, Ah, Al);
-  split_pack_kernel<<<dim3((unsigned)(Kp / 32), (unsigned)(Np / 32)), 256, 0, current_stream()>>>(N, K, (int)Np, (int)Kp, B, ldb, tb ? 0 : 1, Bh, Bl);
+  split_pack_kernel<<<dim3((unsigned)(Kp / 32), (unsigned)(Mp / 32)), 256, 0, current_stream()>>>(nf, M, K, (int)Mp, (int)Kp, A, lda, ta ? 1 : 0, Ah, Al);
+  split_pack_kernel<<<dim3((unsigned)(Kp / 32), (unsigned)(Np / 32)), 256, 0, current_stream()>>>(nf, N, K, (int)Np, (int)Kp, B, ldb, tb ? 0 : 1, Bh, Bl);
   count_launch(2);
   AB_CUDA_CHECK(cudaGetLastError());
   CUtensorMap mAh, mAl, mBh, mBl;
@@ -559,7 +579,8 @@ bool sgemm_tc(int ta, int tb, int M, int N, int K, float alpha, const float* A, 
     AB_CUDA_CHECK(cudaFreeAsync(ws, current_stream()));
     return false;
   }
-  launch_tc<false>(mAh, mAl, mBh, mBl, C, ldc, M, N, (int)(Kp / BK), alpha, beta, cmode, (int)(Mp / BM), (int)(Np / BN), abort_flag, 0.f, 0.f, 0);
+  launch_tc<false>(mAh, mAl, mBh, mBl, C, ldc, M, N, (int)(Kp / BK), alpha, beta, cmode, (int)(Mp / BM), (int)(Np / BN), abort_flag, nf, 0.f, 0.f, 0);
+  (void)sgemm_ffma(ta, tb, M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, cmode, abort_flag, nf);   // runs only if *nf was raised
   AB_CUDA_CHECK(cudaFreeAsync(ws, current_stream()));
   return true;
 }
@@ -592,10 +613,12 @@ bool cgemm_tc(int ta, int ca, int tb, int cb, int M, int N, int K, float2 alpha,
   if (tiles > 0x7fffffffLL) return false;
   float* ws = nullptr;
   keep_pool_cached();
-  AB_CUDA_CHECK(cudaMallocAsync(&ws, bytes, current_stream()));
+  AB_CUDA_CHECK(cudaMallocAsync(&ws, bytes + 64, current_stream()));
   float *Ah = ws, *Al = Ah + Mp * K2, *Bh = Al + Mp * K2, *Bl = Bh + 2 * Np * K2;
-  split_pack_cplx_kernel<<<dim3((unsigned)(Kp / 32), (unsigned)(Mp / 32)), 256, 0, current_stream()>>>(M, K, (int)Mp, (int)Kp, A, lda, ta ? 1 : 0, ca, 0, Ah, Al);
-  split_pack_cplx_kernel<<<dim3((unsigned)(Kp / 32), (unsigned)(Np / 32)), 256, 0, current_stream()>>>(N, K, (int)Np, (int)Kp, B, ldb, tb ? 0 : 1, cb, 1, Bh, Bl);
+  int* nf = reinterpret_cast<int*>(reinterpret_cast<char*>(ws) + bytes);
+  AB_CUDA_CHECK(cudaMemsetAsync(nf, 0, sizeof(int), current_stream()));
+  split_pack_cplx_kernel<<<dim3((unsigned)(Kp / 32), (unsigned)(Mp / 32)), 256, 0, current_stream()>>>(nf, M, K, (int)Mp, (int)Kp, A, lda, ta ? 1 : 0, ca, 0, Ah, Al);
+  split_pack_cplx_kernel<<<dim3((unsigned)(Kp / 32), (unsigned)(Np / 32)), 256, 0, current_stream()>>>(nf, N, K, (int)Np, (int)Kp, B, ldb, tb ? 0 : 1, cb, 1, Bh, Bl);
   count_launch(2);
   AB_CUDA_CHECK(cudaGetLastError());
   CUtensorMap mAh, mAl, mBh, mBl;
@@ -605,7 +628,8 @@ bool cgemm_tc(int ta, int ca, int tb, int cb, int M, int N, int K, float2 alpha,
     return false;
   }
   launch_tc<true>(mAh, mAl, mBh, mBl, reinterpret_cast<float*>(C), ldc, M, N, (int)(K2 / BK), alpha.x, beta.x, cmode, (int)(Mp / BM), (int)(Np / TNc),
-                  abort_flag, alpha.y, beta.y, herk);
+                  abort_flag, nf, alpha.y, beta.y, herk);
+  (void)cgemm_ffma(ta, ca, tb, cb, M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, cmode, herk, abort_flag, nf);
   AB_CUDA_CHECK(cudaFreeAsync(ws, current_stream()));
   return true;
 }

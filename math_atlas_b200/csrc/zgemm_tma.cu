@@ -46,16 +46,11 @@ __device__ __forceinline__ void mbar_expect_tx(uint32_t a, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(a), "r"(bytes) : "memory");
 }
 __device__ __forceinline__ void mbar_arrive(uint32_t a) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(a) : "memory"); }
-// consumer release of a stage: the ld.shared of the stage must have returned and be ordered before the TMA refill
-// (async proxy) that the arrive licenses - see mbar_release in dgemm_tma.cu for the failure this prevents
-__device__ __forceinline__ void mbar_release(uint32_t a, uint32_t dep) {
-#if defined(AB_RELEASE_OLD)
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(a) : "memory");   // round-1 behaviour (racy), measurements only
-#elif AB_RELEASE_FENCE
-  asm volatile("fence.proxy.async.shared::cta;\n\tmbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(a + dep) : "memory");
-#else
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(a + dep) : "memory");
-#endif
+// consumer release of a stage: the ld.shared of the stage must have RETURNED before the arrive that licenses the TMA refill
+// (see mbar_release in dgemm_tma.cu for the failure this prevents): the arrive's address depends on the stage's last
+// fragments, and it is predicated on lane 0 instead of branching
+__device__ __forceinline__ void mbar_release_lane0(uint32_t a, uint32_t dep, int lane) {
+  asm volatile("{\n\t.reg .pred p;\n\tsetp.eq.s32 p, %1, 0;\n\t@p mbarrier.arrive.shared::cta.b64 _, [%0];\n\t}" ::"r"(a + dep), "r"(lane) : "memory");
 }
 __device__ __forceinline__ void mbar_wait(uint32_t a, uint32_t parity) {
   uint32_t done;
@@ -203,8 +198,7 @@ zgemm_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             dmma884(ci[mi][ni][0], ci[mi][ni][1], ai[mi], br[ni]);
           }
       }
-      __syncwarp();
-      if (lane == 0) mbar_release(bar_base + 8 * (STAGES + s), dep & zero_rt);
+      mbar_release_lane0(bar_base + 8 * (STAGES + s), dep & zero_rt, lane);
     }
 
     // ---- epilogue: C = alpha*acc + beta*C (complex), triangle mask, HERK real diagonal ----

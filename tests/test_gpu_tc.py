@@ -62,3 +62,26 @@ def test_tc_syrk_herk(oracle, pre):
             assert np.all(got[:N][np.arange(N), np.arange(N)].imag == 0)
             other = np.triu_indices(N, 1) if uplo == Lower else np.tril_indices(N, -1)
             assert np.array_equal(got[:N][other], C0[:N][other])
+
+
+@pytest.mark.gpu
+def test_tensor_core_sgemm_nonfinite_and_near_overflow_operands():
+    """the 3xTF32 split computed lo = a - tf32(a), which is NaN for a = Inf and for finite a that rounds up to Inf
+    in TF32; the product then became NaN where FP32 SGEMM (the reference) gives Inf or a finite value."""
+    import numpy as np
+    import math_atlas_b200 as ab
+    M, N, K = 256, 256, 512
+    rng = np.random.default_rng(1)
+    A = np.asfortranarray((rng.random((M, K)) + 0.5).astype(np.float32))
+    B = np.asfortranarray((rng.random((K, N)) + 0.5).astype(np.float32))
+    C = np.zeros((M, N), dtype=np.float32, order="F")
+    A[3, 5] = np.inf                      # row 3 of C must be +Inf (all of B is positive), nothing may be NaN
+    A[7, 9] = np.float32(3.4028234e38)    # FLT_MAX rounds to Inf in TF32; times 1e-30 it is a small finite number
+    B[9, :] = np.float32(1e-30)
+    ab.cblas_sgemm(ab.CblasColMajor, ab.CblasNoTrans, ab.CblasNoTrans, M, N, K, 1.0, A, M, B, K, 0.0, C, M)
+    assert not np.isnan(C).any()
+    assert np.all(np.isposinf(C[3]))
+    fin = np.delete(C, 3, axis=0)
+    assert np.isfinite(fin).all()
+    ref = (A.astype(np.float64) @ B.astype(np.float64))
+    assert np.allclose(C[7], ref[7], rtol=1e-5)
