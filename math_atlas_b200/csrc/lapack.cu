@@ -734,7 +734,10 @@ static void getrf_rec(T* A0, size_t lda, int r0, int M, int N, int* d_ipiv, int*
   // nodes up to ATLB200_LU_PW columns are factored right-looking by getrf_panel (3 launches per leaf width);
   // above that the reference's recursion keeps the updates as large-K GEMMs
   static const int pw_short = env_int("ATLB200_LU_PW", 512);
-  static const int pw_tall = env_int("ATLB200_LU_PW_TALL", pw_short);   // panels whose leaves are half width (more rows than one full-width cluster holds)
+  // panels whose leaves are half width (more rows than one full-width cluster holds) recurse down to 128 columns: their
+  // rank-b updates run on the one reserved GPC beside the trailing GEMM, where a few large-K GEMMs beat many K=16 ones
+  // (N=16384: 149 -> 143 ms, profiles/r02_lu_phases.txt)
+  static const int pw_tall = env_int("ATLB200_LU_PW_TALL", pw_short < 128 ? pw_short : 128);
   const int pw = (leaf_w < PanelW<T>::W) ? pw_tall : pw_short;
   if (N <= max(leaf_w, pw)) {
     getrf_panel<T>(A0, lda, r0, M, N, d_ipiv, d_info);
@@ -1278,7 +1281,8 @@ static void potrf_lookahead(int uplo, int N, T* A, size_t lda, int* d_info, int 
 template <typename T>
 void potrf(int uplo, int N, T* A, size_t lda, int* d_info) {
   AB_CUDA_CHECK(cudaMemsetAsync(d_info, 0, sizeof(int), current_stream()));
-  const int NB = env_int("ATLB200_LLT_NB", 512);
+  // block size: 512, 256 up to N = 8192 where the diagonal-block chain bounds most steps (N=8192: 20.3 -> 18.3 ms; N=16384: 69.8 vs 73.3)
+  const int NB = env_int("ATLB200_LLT_NB", N <= 8192 ? 256 : 512);
   if (env_int("ATLB200_LU_LOOKAHEAD", 1) && NB > 0 && N >= 4 * NB) potrf_lookahead<T>(uplo, N, A, lda, d_info, NB);
   else potrf_rec<T>(uplo, N, A, lda, d_info, 0);
 }
