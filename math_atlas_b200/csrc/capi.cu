@@ -245,11 +245,19 @@ static bool atl_gemm_pipelined(int TA, int TB, size_t M, size_t N, size_t K, T a
     AB_CUDA_CHECK(cudaEventRecord(cs.a_in, cs.h2d));
     AB_CUDA_CHECK(cudaStreamWaitEvent(U, cs.a_in, 0));
   }
-  for (int j = j0; j < np; j++) {
+  // The upload of panel j+1 is issued BEFORE the download of panel j: with pageable host memory (what malloc / numpy callers
+  // pass) a D2H copy returns only when it has completed, i.e. after GEMM j, and issuing the next upload behind it would
+  // serialise the whole pipeline.
+  auto upload = [&](int j) {
     const size_t c0 = (size_t)j * pw, nc = std::min(pw, N - c0);
     h2d_B(c0, nc, 0, K);
     h2d_C(c0, nc);
     AB_CUDA_CHECK(cudaEventRecord(cs.in[j], cs.h2d));
+  };
+  if (j0 < np) upload(j0);
+  for (int j = j0; j < np; j++) {
+    const size_t c0 = (size_t)j * pw, nc = std::min(pw, N - c0);
+    if (j + 1 < np) upload(j + 1);
     AB_CUDA_CHECK(cudaStreamWaitEvent(U, cs.in[j], 0));
     gemm<T>(TA, TB, (int)M, (int)nc, (int)K, alpha, a.d, a.ld, tB ? dB + c0 : dB + c0 * ldbd, ldbd, beta, dC + c0 * ldcd, ldcd);
     d2h_C(j, c0, nc);
