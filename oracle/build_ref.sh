@@ -97,5 +97,20 @@ if [ -f "$LIB200/libatlas_b200.so" ]; then
 else
   echo "build_ref: libatlas_b200.so not built yet - tester programs skipped"
 fi
+# 4. The reference's hand-tuned AVX-512 access-major DGEMM micro-kernel (kernel/ClintWhaley/ATL_damm24x8x1_avxz.S, index entry
+#    Clint/atlas-ammm.base:129-131) assembled from where it lies, BETA0 and BETA1 variants, under oracle/ref_shim/tuned_dgemm.c
+#    (ours: the copy / K-loop / write-back / threading a tuned build would run, with fixed blocking) -> libatltuned.so = the
+#    "tuned reference" CPU baseline of bench.py.  The kernel was written for the first 512-bit ISA (Xeon Phi): its vprefetch{0,1,2}
+#    mnemonics are spelled prefetcht{0,1,2} on AVX-512 CPUs; every arithmetic / load / store instruction is AVX-512F as written.
+KDIR="$REF/AtlasBase/kernel/ClintWhaley"
+if [ -f "$KDIR/ATL_damm24x8x1_avxz.S" ]; then
+  for b in 0 1; do
+    gcc -x assembler-with-cpp -c -I$A/include -DATL_GAS_x8664 -DDREAL -DBETA$b -DATL_USERMM=ref_damm24x8_b$b \
+        -Dvprefetch0=prefetcht0 -Dvprefetch1=prefetcht1 -Dvprefetch2=prefetcht2 -Dvprefetchw=prefetchw \
+        "$KDIR/ATL_damm24x8x1_avxz.S" -o obj_k_b$b.o
+  done
+  gcc -O2 -fPIC -shared -Wl,-z,noexecstack -o "$OUT/libatltuned.so" "$HERE/ref_shim/tuned_dgemm.c" obj_k_b0.o obj_k_b1.o -lpthread \
+    && echo "build_ref: built $OUT/libatltuned.so"
+fi
 cd "$HERE"; rm -rf "$W"
 echo "build_ref: built $OUT/libatlref.so"

@@ -43,7 +43,8 @@ def build_ref():
     """Build oracle/_ref/libatlref.so if /root/reference is present; returns path or None."""
     so = os.path.join(HERE, "_ref", "libatlref.so")
     testers = os.path.join(HERE, "_ref", "bin", "xdl3blastst")   # the reference's tester programs linked to our library
-    if (not os.path.exists(so) or not os.path.exists(testers)) and os.path.exists("/root/reference/extract.c"):
+    tuned = os.path.join(HERE, "_ref", "libatltuned.so")         # the reference's AVX-512 amm micro-kernel + our driver (CPU baseline)
+    if (not os.path.exists(so) or not os.path.exists(testers) or not os.path.exists(tuned)) and os.path.exists("/root/reference/extract.c"):
         subprocess.check_call(["bash", os.path.join(HERE, "build_ref.sh")])
     return so if os.path.exists(so) else None
 
@@ -184,6 +185,30 @@ class Oracle(_Base):
     def getri(self, pre, order, N, a, ipiv, nb=4):
         ipiv = np.ascontiguousarray(ipiv, dtype=np.int32)
         return getattr(self.lib, f"orc_{pre}getri")(N, _p(a), self._ld(a), _p(ipiv), nb)
+
+
+class Tuned:
+    """oracle/_ref/libatltuned.so: threaded host DGEMM on the reference's hand-tuned AVX-512 access-major micro-kernel
+    (ATL_damm24x8x1_avxz.S, assembled from /root/reference by build_ref.sh) under oracle/ref_shim/tuned_dgemm.c.
+    CPU baseline of bench.py and a cross-check in tests; raises when the library is absent or the CPU has no AVX-512."""
+
+    def __init__(self):
+        build_ref()
+        so = os.path.join(HERE, "_ref", "libatltuned.so")
+        if not os.path.exists(so):
+            raise FileNotFoundError("oracle/_ref/libatltuned.so not built")
+        self.lib = C.CDLL(so)
+        self.lib.atltuned_dgemm.argtypes = [C.c_int] * 5 + [C.c_double, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_double, C.c_void_p,
+                                                          C.c_int] + [C.c_int] * 4
+        if not self.lib.atltuned_have_avx512():
+            raise RuntimeError("host CPU has no AVX-512: the reference's avxz micro-kernel cannot run")
+
+    def dgemm(self, TA, TB, M, N, K, alpha, A, lda, B, ldb, beta, Cm, ldc, threads=1, blocking=(0, 0, 0)):
+        """column-major; TA/TB 0 = NoTrans, 1 = Trans; A, B, Cm numpy arrays (or raw addresses)"""
+        ad = lambda x: x if isinstance(x, int) else x.ctypes.data
+        rc = self.lib.atltuned_dgemm(TA, TB, M, N, K, alpha, ad(A), lda, ad(B), ldb, beta, ad(Cm), ldc, threads, *blocking)
+        if rc != 0:
+            raise RuntimeError(f"atltuned_dgemm failed ({rc})")
 
 
 class Ref(_Base):
