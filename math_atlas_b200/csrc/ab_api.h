@@ -86,6 +86,8 @@ void conj_inplace(int M, int N, T* B, size_t ldb);
 
 // large GEMMs launched by this host thread stay off n SMs (<= 16, one GPC) while n > 0 (see lapack.cu)
 void lu_reserve_sms(int n);
+// 1 if an M-row LU panel of type pre (s/d/c/z) runs on the cluster leaf, i.e. can be factored beside an update GEMM that keeps a GPC free
+int lu_panel_overlaps(char pre, int M);
 // diagnostic: copies the 3 checksums per block step of the last getrf run with ATLB200_LU_CHECKSUM=1; returns the step count
 int lu_checksums(double* host_out, int max_steps);
 

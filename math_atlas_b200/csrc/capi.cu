@@ -830,6 +830,7 @@ CPLX_API(z, cdouble, double, "Z")
 extern "C" {
 void atlb200_set_async(int on) { g_async = on; }
 void atlb200_reserve_sms(int n) { lu_reserve_sms(n); }
+int atlb200_lu_panel_overlaps(char pre, int M) { return lu_panel_overlaps(pre, M); }
 int atlb200_lu_checksums(double* out, int max_steps) { return lu_checksums(out, max_steps); }
 #define DEV_API(P, T)                                                                                              \
   void atlb200_##P##getrf_dev(int M, int N, void* A, size_t lda, int* d_ipiv, int* d_info) {                       \

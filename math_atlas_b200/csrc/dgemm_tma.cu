@@ -393,7 +393,9 @@ thread_local SmMask g_reserved = {{0, 0, 0, 0}};
 thread_local bool g_reserved_on = false;
 thread_local int* g_counters[AB_MAX_DEV] = {};   // ring of device tile counters, one ring per device
 thread_local int g_counter_next = 0;
-constexpr int NCOUNTERS = 256;
+// (a counter is zeroed in stream order right before its launch and must not be reused while that launch is pending: the host
+//  runs at most ~1000 launches ahead of the device)
+constexpr int NCOUNTERS = 8192;
 
 template <bool AK, bool BK_, int NI>
 void launch(const CUtensorMap& ta, const CUtensorMap& tb, double* C, size_t ldc, int M, int N, int K, double alpha,

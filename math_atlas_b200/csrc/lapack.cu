@@ -142,12 +142,90 @@ __global__ void __launch_bounds__(64) laswp_kernel(int N, T* A, size_t lda, int 
   }
 }
 
+// Forward interchanges with unit pivot stride, the form every factorisation step uses (ATL_laswp, atlas-lp.base:310 ff.).
+// laswp_kernel above walks a column with ONE thread, so a 512-pivot pass over the 512 columns of the next panel keeps 8 SMs
+// busy for 0.4 ms - on the critical path of every LU block step.  Here a column belongs to TPC threads of one warp and the
+// pivots are taken 32 at a time: every warp composes the 32 sequential swaps into a permutation in registers (the scheme of
+// swap_trsm_kernel below: lane i follows top position i, lane k the k-th displaced row; any aliasing between the swaps is
+// handled by the composition itself), then all gathers of the batch are issued, then all stores.  The composition of batch
+// j+1 overlaps the loads of batch j.  512 pivots x 512 columns: 0.42 ms -> ~0.05 ms.
+template <typename T, int TPC>
+__global__ void __launch_bounds__(64) laswp_par_kernel(int N, T* A, size_t lda, int K1, int K2, const int* piv) {
+  constexpr int CPW = 32 / TPC;            // columns per warp
+  constexpr int EPT = 32 / TPC;            // top (and displaced) entries per thread
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int col = (blockIdx.x * 2 + wid) * CPW + lane / TPC;
+  const int q = lane % TPC;
+  const bool live = col < N;
+  T* bp = A + (size_t)(live ? col : 0) * lda;
+  int cur, orow, ocur, cnt;
+  auto compose = [&](int row0, int b) {
+    cur = row0 + lane; orow = -1; ocur = -1; cnt = 0;
+    const int myp = (lane < b) ? piv[row0 + lane] : -1;
+    for (int i = 0; i < b; i++) {
+      const int p = __shfl_sync(0xffffffffu, myp, i);
+      const int ci = __shfl_sync(0xffffffffu, cur, i);
+      if (p == row0 + i) continue;                       // uniform
+      if (p < row0 + b) {                                // target inside the batch's own rows
+        const int cp = __shfl_sync(0xffffffffu, cur, p - row0);
+        if (lane == i) cur = cp;
+        if (lane == p - row0) cur = ci;
+      } else {
+        const unsigned hit = __ballot_sync(0xffffffffu, orow == p);
+        int k;
+        if (hit) k = __ffs(hit) - 1;
+        else { k = cnt; if (lane == k) { orow = p; ocur = p; } cnt++; }
+        const int co = __shfl_sync(0xffffffffu, ocur, k);
+        if (lane == i) cur = co;
+        if (lane == k) ocur = ci;
+      }
+    }
+  };
+  compose(K1, min(32, K2 - K1));
+  for (int i0 = K1; i0 < K2; i0 += 32) {
+    const int b = min(32, K2 - i0), nout = cnt;
+    int ts[EPT], orw[EPT], osr[EPT];
+#pragma unroll
+    for (int m = 0; m < EPT; m++) {
+      const int e = m * TPC + q;
+      ts[m] = __shfl_sync(0xffffffffu, cur, e);
+      orw[m] = __shfl_sync(0xffffffffu, orow, e);
+      osr[m] = __shfl_sync(0xffffffffu, ocur, e);
+    }
+    T x[EPT], o[EPT];
+#pragma unroll
+    for (int m = 0; m < EPT; m++) {
+      const int e = m * TPC + q;
+      if (live && e < b && ts[m] != i0 + e) x[m] = bp[ts[m]];
+      if (live && e < nout) o[m] = bp[osr[m]];
+    }
+    if (i0 + 32 < K2) compose(i0 + 32, min(32, K2 - i0 - 32));     // overlaps the loads above
+    __syncwarp();                       // the threads of a column are in one warp: every gather precedes every store
+#pragma unroll
+    for (int m = 0; m < EPT; m++) {
+      const int e = m * TPC + q;
+      if (live && e < b && ts[m] != i0 + e) bp[i0 + e] = x[m];
+      if (live && e < nout) bp[orw[m]] = o[m];
+    }
+    __syncwarp();                       // ... and every store of this batch the next batch's gathers
+  }
+}
+
 template <typename T>
 static void laswp_blocks(int N, T* A, size_t lda, int K1, int K2, const int* d_piv, int inci, int k1_step) {
   if (N <= 0 || K2 <= K1) return;
 #ifdef ATLB200_DIAG
   if (diag::on_side() && (diag::pnop() & 2)) return;
 #endif
+  static const int par = env_int("ATLB200_LASWP_PAR", 1);
+  if (par && inci == 1 && k1_step == 0 && K2 - K1 >= 8) {
+    // narrow column sets: 16 threads per column (more CTAs); wide ones: 8 threads per column
+    if (N <= 4096) laswp_par_kernel<T, 16><<<(N + 3) / 4, 64, 0, current_stream()>>>(N, A, lda, K1, K2, d_piv);
+    else laswp_par_kernel<T, 8><<<(N + 7) / 8, 64, 0, current_stream()>>>(N, A, lda, K1, K2, d_piv);
+    count_launch();
+    AB_CUDA_CHECK(cudaGetLastError());
+    return;
+  }
   const int threads = 64;
   laswp_kernel<T><<<(N + threads - 1) / threads, threads, 0, current_stream()>>>(N, A, lda, K1, K2, d_piv, inci, k1_step);
   count_launch();
@@ -684,6 +762,29 @@ static void getf2_leaf(int M, int w, int lw, bool use_cluster, T* A, size_t lda,
   else cluster_launch<T, E / 4, 4>(M, w, A, lda, d_ipiv, d_info, piv_off, info_off);
 }
 
+namespace {
+struct SideStream {
+  cudaStream_t st = nullptr, aux = nullptr;
+  cudaEvent_t cols[2] = {nullptr, nullptr}, panel[2] = {nullptr, nullptr}, have[2] = {nullptr, nullptr}, solved[2] = {nullptr, nullptr};
+
+  int dev = -1;
+  void ensure() {
+    int d; AB_CUDA_CHECK(cudaGetDevice(&d));
+    if (st && d == dev) return;
+    dev = d;
+    AB_CUDA_CHECK(cudaStreamCreateWithPriority(&st, cudaStreamNonBlocking, env_int("ATLB200_LU_SIDE_PRIO", -1)));   // panel work first
+    AB_CUDA_CHECK(cudaStreamCreateWithFlags(&aux, cudaStreamNonBlocking));
+    for (int i = 0; i < 2; i++) {
+      AB_CUDA_CHECK(cudaEventCreateWithFlags(&cols[i], cudaEventDisableTiming));
+      AB_CUDA_CHECK(cudaEventCreateWithFlags(&panel[i], cudaEventDisableTiming));
+      AB_CUDA_CHECK(cudaEventCreateWithFlags(&have[i], cudaEventDisableTiming));
+      AB_CUDA_CHECK(cudaEventCreateWithFlags(&solved[i], cudaEventDisableTiming));
+    }
+  }
+};
+thread_local SideStream g_side;
+}  // namespace
+
 // ---- right-looking panel: leaf / fused interchange+solve / rank-b update ---------------------------------------
 // Factor the M x w panel (w <= a few hundred columns) whose top-left corner is (r0, r0) of A0.  The reference
 // recurses down to single columns (ATL_getrfC -> LU2/getf2, atlas-lp.base:1497-1617, 1301); on the GPU every
@@ -769,28 +870,6 @@ static void getrf_rec(T* A0, size_t lda, int r0, int M, int N, int* d_ipiv, int*
 // is factored (recursively, on the side stream) as soon as its own columns have received update k,
 // while the main stream applies update k to the rest of the trailing matrix.  Pivoting is
 // unchanged (the same column-by-column search on the same updated values).
-namespace {
-struct SideStream {
-  cudaStream_t st = nullptr, aux = nullptr;
-  cudaEvent_t cols[2] = {nullptr, nullptr}, panel[2] = {nullptr, nullptr}, have[2] = {nullptr, nullptr}, solved[2] = {nullptr, nullptr};
-
-  int dev = -1;
-  void ensure() {
-    int d; AB_CUDA_CHECK(cudaGetDevice(&d));
-    if (st && d == dev) return;
-    dev = d;
-    AB_CUDA_CHECK(cudaStreamCreateWithPriority(&st, cudaStreamNonBlocking, env_int("ATLB200_LU_SIDE_PRIO", -1)));   // panel work first
-    AB_CUDA_CHECK(cudaStreamCreateWithFlags(&aux, cudaStreamNonBlocking));
-    for (int i = 0; i < 2; i++) {
-      AB_CUDA_CHECK(cudaEventCreateWithFlags(&cols[i], cudaEventDisableTiming));
-      AB_CUDA_CHECK(cudaEventCreateWithFlags(&panel[i], cudaEventDisableTiming));
-      AB_CUDA_CHECK(cudaEventCreateWithFlags(&have[i], cudaEventDisableTiming));
-      AB_CUDA_CHECK(cudaEventCreateWithFlags(&solved[i], cudaEventDisableTiming));
-    }
-  }
-};
-thread_local SideStream g_side;
-}  // namespace
 
 template <typename T>
 static void lu_apply_panel(T* A, size_t lda, int M, int k0, int w, int c0, int nc, const int* d_ipiv, int ph0 = PH_REST_SWAP) {
@@ -903,13 +982,21 @@ static void getrf_lookahead(int M, int N, T* A, size_t lda, int* d_ipiv, int* d_
   cudaStream_t U = current_stream(), P = ss.st;
   // SMs of one GPC are kept free of update-GEMM CTAs while a panel is being factored beside it; from block step
   // ATLB200_LU_RESERVE2_PCT % of the way on - when the panel chain, not the update, bounds a step - two GPCs
-  const bool res_on = env_int("ATLB200_LU_RESERVE", 1) != 0;
-  const int res2_pct = env_int("ATLB200_LU_RESERVE2_PCT", 100);
-  const unsigned long long* res1 = res_on ? cluster_reserved_mask(1) : nullptr;
-  const unsigned long long* res2 = (res_on && res2_pct < 100) ? cluster_reserved_mask(2) : nullptr;
-  const int total_steps = (MN + NB - 1) / NB;
   // ATLB200_LU_TRACE=1: both streams per block step; 2: every phase (LuTracer)
   const int trace = env_int("ATLB200_LU_TRACE", 0);
+  const bool res_on = env_int("ATLB200_LU_RESERVE", 1) != 0;
+  const int res2_pct = env_int("ATLB200_LU_RESERVE2_PCT", 20);
+  const unsigned long long* res1 = res_on ? cluster_reserved_mask(1) : nullptr;
+  const unsigned long long* res2 = (res_on && res2_pct < 100) ? cluster_reserved_mask(2) : nullptr;
+  unsigned long long res12[4] = {0, 0, 0, 0};       // two GPCs, certainly including the one of res1
+  if (res2 && !cluster_two_gpc_mask(res1, res12)) res2 = nullptr;
+  if (trace && res1) {
+    int n1 = 0, n2 = 0;
+    for (int i = 0; i < 4; i++) { n1 += __builtin_popcountll(res1[i]); n2 += __builtin_popcountll(res12[i]); }
+    fprintf(stderr, "# getrf look-ahead: %d SMs reserved for the panel chain, %d once two GPCs are\n", n1, n2);
+  }
+
+  const int total_steps = (MN + NB - 1) / NB;
   g_lutr.on = trace >= 2;
   std::vector<cudaEvent_t> tev;
   auto mark = [&](cudaStream_t st) { if (trace) { cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, st); tev.push_back(e); } };
@@ -955,9 +1042,29 @@ static void getrf_lookahead(int M, int N, T* A, size_t lda, int* d_ipiv, int* d_
       const int c0 = c1 + w1, nc = nright - w1;
       T* Akk = A + (size_t)k0 + (size_t)k0 * lda;
       const bool aux_step = use_aux && more && nc > 0;
+      if (more) {
+        // next panel's columns first.  Their interchanges run ALONE: R's pass over the rest columns (14 000 columns of
+        // 32-byte-sector traffic) starts behind them - side by side the narrow pass took 0.22 ms instead of 0.05 - and then
+        // shares the GPU with the next panel's solve and update, which do not compete for the same resource.
+        g_lutr.begin(PH_NEXT_SWAP);
+        laswp<T>(w1, A + (size_t)c1 * lda, lda, k0, k0 + w, d_ipiv, 1);
+        g_lutr.end();
+      }
+      if (aux_step) AB_CUDA_CHECK(cudaEventRecord(ss.have[k & 1], U));
+      if (more) {
+        g_lutr.begin(PH_NEXT_TRSM);
+        trsm<T>(Left, Lower, NoTrans, Unit, w, w1, S::one(), Akk, lda, A + (size_t)k0 + (size_t)c1 * lda, lda);
+        g_lutr.end();
+        if (M - k0 - w > 0) {
+          g_lutr.begin(PH_NEXT_GEMM);
+          gemm<T>(NoTrans, NoTrans, M - k0 - w, w1, w, S::from_real(-1), A + (size_t)(k0 + w) + (size_t)k0 * lda, lda,
+                  A + (size_t)k0 + (size_t)c1 * lda, lda, S::one(), A + (size_t)(k0 + w) + (size_t)c1 * lda, lda);
+          g_lutr.end();
+        }
+        AB_CUDA_CHECK(cudaEventRecord(ss.cols[k & 1], U));
+      }
       if (aux_step) {
         // R: interchanges and U block row of the rest columns, beside the next panel's update on U
-        AB_CUDA_CHECK(cudaEventRecord(ss.have[k & 1], U));
         AB_CUDA_CHECK(cudaStreamWaitEvent(R, ss.have[k & 1], 0));
         set_current_stream(R);
         g_lutr.begin(PH_REST_SWAP);
@@ -970,14 +1077,13 @@ static void getrf_lookahead(int M, int N, T* A, size_t lda, int* d_ipiv, int* d_
         set_current_stream(U);
       }
       if (more) {
-        lu_apply_panel<T>(A, lda, M, k0, w, c1, w1, d_ipiv, PH_NEXT_SWAP);    // next panel's columns first
-        AB_CUDA_CHECK(cudaEventRecord(ss.cols[k & 1], U));
         AB_CUDA_CHECK(cudaStreamWaitEvent(P, ss.cols[k & 1], 0));
         set_current_stream(P);
         mark(P);
 #ifdef ATLB200_DIAG
         diag::on_side() = true;
 #endif
+        const bool two_gpc = res2 && k * 100 >= total_steps * res2_pct;
         getrf_rec<T>(A, lda, c1, M - c1, w1, d_ipiv, d_info);        // panel k+1 beside the update
 #ifdef ATLB200_DIAG
         diag::on_side() = false;
@@ -985,7 +1091,7 @@ static void getrf_lookahead(int M, int N, T* A, size_t lda, int* d_ipiv, int* d_
         mark(P);
         AB_CUDA_CHECK(cudaEventRecord(ss.panel[k & 1], P));
         set_current_stream(U);
-        set_gemm_reserved((res2 && k * 100 >= total_steps * res2_pct) ? res2 : res1);   // leave a GPC (or two) to the panel kernels
+        set_gemm_reserved(two_gpc ? res12 : res1);   // leave a GPC (or two) to the panel kernels
       }
       // The rest of update k (interchanges, U block row, Schur complement) runs beside the panel.  (Round 1
       // shipped with the TRSM+GEMM held back until the panel had finished, because ~2 % of the runs changed
@@ -1083,6 +1189,20 @@ void lu_reserve_sms(int n) {
   for (int i = 0; i < 256 && taken < n; i++)
     if (full[i >> 6] >> (i & 63) & 1ull) { m[i >> 6] |= 1ull << (i & 63); taken++; }
   set_gemm_reserved(m);
+}
+
+// Can a panel of M rows be factored beside a running update GEMM?  Only the cluster leaf can (it needs the 16 SMs of one
+// GPC); taller panels use the cooperative global-barrier kernel, whose CTAs must all be co-resident (multi-GPU drivers ask).
+int lu_panel_overlaps(char pre, int M) {
+  bool cl = false;
+  switch (pre) {
+    case 's': (void)leaf_width_for<float>(M, &cl); break;
+    case 'd': (void)leaf_width_for<double>(M, &cl); break;
+    case 'c': (void)leaf_width_for<float2>(M, &cl); break;
+    case 'z': (void)leaf_width_for<double2>(M, &cl); break;
+    default: return 0;
+  }
+  return cl ? 1 : 0;
 }
 
 template <typename T>

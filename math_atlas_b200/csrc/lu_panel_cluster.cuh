@@ -499,9 +499,10 @@ __global__ void __launch_bounds__(CL_TPB, 1) cluster_probe_kernel(unsigned* smid
 // nclusters = 1 or 2: the SMs of one GPC, or of two (the look-ahead gives the panel chain a second GPC once the
 // factorisation has become panel-bound).  Probed once per device.
 static const unsigned long long* cluster_reserved_mask(int nclusters = 1) {
-  struct Entry { unsigned long long mask[4] = {0, 0, 0, 0}; bool done = false, ok = false; };
+  struct Entry { unsigned long long mask[4] = {0, 0, 0, 0}, second[4] = {0, 0, 0, 0}; bool done = false, ok = false; };
   static Entry table[AB_MAX_DEV][2];
-  nclusters = nclusters >= 2 ? 2 : 1;
+  const bool want_second = nclusters == -2;
+  nclusters = (nclusters >= 2 || want_second) ? 2 : 1;
   Entry& e = table[ab_dev()][nclusters - 1];
   if (!e.done) {
     e.done = true;
@@ -525,12 +526,31 @@ static const unsigned long long* cluster_reserved_mask(int nclusters = 1) {
         unsigned h[2 * CL_MAXC];
         AB_CUDA_CHECK(cudaMemcpy(h, d, c * nclusters * sizeof(unsigned), cudaMemcpyDeviceToHost));
         for (int i = 0; i < c * nclusters; i++) if (h[i] < 256) e.mask[h[i] >> 6] |= 1ull << (h[i] & 63);
+        for (int i = c; i < c * nclusters; i++) if (h[i] < 256) e.second[h[i] >> 6] |= 1ull << (h[i] & 63);
         e.ok = true;
       } else (void)cudaGetLastError();
     }
     cudaFree(d);
   }
+  if (want_second) return e.ok ? e.second : nullptr;
   return e.ok ? e.mask : nullptr;
+}
+
+// A second GPC for the panel chain, disjoint from cluster_reserved_mask(1) = `a`: of the two clusters of the two-cluster probe,
+// the one that shares fewer SMs with `a`.  out = a | that cluster.
+static bool cluster_two_gpc_mask(const unsigned long long* a, unsigned long long* out) {
+  const unsigned long long* both = cluster_reserved_mask(2);
+  if (!a || !both) return false;
+  const unsigned long long* second = cluster_reserved_mask(-2);
+  unsigned long long first[4];
+  int ov1 = 0, ov2 = 0;
+  for (int i = 0; i < 4; i++) {
+    first[i] = both[i] & ~second[i];
+    ov1 += __builtin_popcountll(first[i] & a[i]);
+    ov2 += __builtin_popcountll(second[i] & a[i]);
+  }
+  for (int i = 0; i < 4; i++) out[i] = a[i] | (ov1 <= ov2 ? first[i] : second[i]);
+  return true;
 }
 
 // largest cluster size (power of two <= 16) this kernel can be launched with on the current device

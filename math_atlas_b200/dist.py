@@ -126,6 +126,11 @@ class CudaOps:
             n = int(os.environ.get("ATLB200_DIST_RESERVE", n))
         self.L.atlb200_reserve_sms(n)
 
+    def panel_overlaps(self, M):
+        """can an M-row LU panel be factored on a side stream beside this rank's update GEMM?  (Only the cluster leaf can; the
+        cooperative kernel of taller panels needs all its CTAs co-resident and must have the GPU to itself.)"""
+        return bool(self.L.atlb200_lu_panel_overlaps(C.c_char(self.pre.encode()), int(M)))
+
     def getrf(self, M, N, a, lda, piv, info):
         getattr(self.L, f"atlb200_{self.pre}getrf_dev")(M, N, a, lda, piv.data_ptr(), info.data_ptr())
 
@@ -304,9 +309,12 @@ def pgetrf(pre, M, lay, A_loc, ld, ops, group=None, lookahead=True):
             w1 = lay.width(k + 1)
             update(k, P, piv, t0, t0 + w1)          # bring the next panel up to date first ...
             mark(k, "next_cols")
-            if side is not None:
+            use_side = side is not None and (not hasattr(ops, "panel_overlaps") or ops.panel_overlaps(geom(k + 1)[3]))
+            if use_side:
                 # ... factor it and start its broadcast on a second, high-priority stream, so that this rank's own trailing
-                # update runs BESIDE its panel (round 1 ran them in line: the owner's panel + update bounded every step)
+                # update runs BESIDE its panel (round 1 ran them in line: the owner's panel + update bounded every step).
+                # Panels too tall for the cluster leaf stay in line: their cooperative kernel and the persistent update GEMM
+                # fight for SMs (2-GPU N=65536: 6.6 s with the side stream for every panel)
                 side.wait_stream(torch.cuda.current_stream())
                 ops.use_stream(side)
                 with torch.cuda.stream(side):
@@ -316,7 +324,7 @@ def pgetrf(pre, M, lay, A_loc, ld, ops, group=None, lookahead=True):
                 nbuf, nwork = post(k + 1)           # ... factor it and start its broadcast ...
             mark(k, "factored")
             if overlap:
-                ops.reserve(16 if side is not None else 8)   # room for the panel's cluster / the broadcast's kernels beside the GEMM
+                ops.reserve(16 if use_side else 8)   # room for the panel's cluster / the broadcast's kernels beside the GEMM
             update(k, P, piv, t0 + w1, lay.ncols_local)   # ... which overlaps the rest of the update
             if overlap:
                 ops.reserve(-1)
