@@ -15,6 +15,7 @@
 // device arrays are used in place.  Every call returns after the stream has drained (BLAS has no
 // asynchronous contract).  There is no CPU fallback: without a CUDA device the first call aborts.
 #include "ab_api.h"
+#include "dgemm_tma.h"
 #include <cstdarg>
 #include <cstring>
 #include <cctype>
@@ -392,7 +393,9 @@ static void atl_gemm(int TA, int TB, size_t M, size_t N, size_t K, T alpha, cons
   Operand<T> a(A, needAB ? (int)(tA ? K : M) : 0, needAB ? (int)(tA ? M : K) : 0, lda, true, false);
   Operand<T> b(B, needAB ? (int)(tB ? N : K) : 0, needAB ? (int)(tB ? K : N) : 0, ldb, true, false);
   Operand<T> c(C, (int)M, (int)N, ldc, !ST<T>::is_zero(beta), true);
+  set_gemm_splitk_allowed(true);
   gemm<T>(TA, TB, (int)M, (int)N, (int)K, alpha, a.d, a.ld, b.d, b.ld, beta, c.d, c.ld);
+  set_gemm_splitk_allowed(false);
   a.finish(); b.finish(); c.finish();
   sync_stream();
 }

@@ -20,6 +20,7 @@
 //   MN-major tile [k][16 m] per 16-row group (A, B^T): position = ((((m&15)>>1) ^ (k&7))<<1) | (m&1)
 #include "common.cuh"
 #include "dgemm_tma.h"
+namespace ab { void keep_pool_cached(); }
 #include <cuda.h>
 #include <mutex>
 #include <cstdlib>
@@ -161,7 +162,7 @@ __global__ void __launch_bounds__(THREADS, 1)
 dgemm_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                  double* __restrict__ C, size_t ldc, int M, int N, int K, double alpha, double beta,
                  int cmode, int tiles_m, int tiles_n, const int* abort_flag,
-                 const SmMask reserved, int* tile_counter) {
+                 const SmMask reserved, int* tile_counter, int ksplit, int Ks, double* __restrict__ Wsplit) {
   if (abort_flag && *abort_flag) return;  // POTRF stop-at-first-failure (uniform for the whole grid)
   {
     const unsigned sm = my_smid();
@@ -184,8 +185,12 @@ dgemm_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   }
   __syncthreads();
 
-  const int KT = (K + BK - 1) / BK;
-  const int ntiles = tiles_m * tiles_n;
+  // split-K (ksplit > 1, small problems only - see launch()): work item = (k slice, tile); slice q covers k in
+  // [q*Ks, min(K, (q+1)*Ks)) (Ks a multiple of BK) and writes its partial product to Wsplit + q*M*N (leading dimension M);
+  // splitk_reduce_kernel then adds the slices in a fixed order, so the result does not depend on the schedule.
+  const int mn_tiles = tiles_m * tiles_n;
+  const int ntiles = mn_tiles * ksplit;
+  auto kt_of = [&](int q) { return ksplit > 1 ? (min(K, (q + 1) * Ks) - q * Ks + BK - 1) / BK : (K + BK - 1) / BK; };
 
   if (warp == CONS_WARPS) {
     // ===================== TMA producer warp =====================
@@ -197,11 +202,13 @@ dgemm_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       else { tile = next_static; next_static += gridDim.x; }
       const bool done = tile >= ntiles;
       int m0 = 0, n0 = 0;
+      const int q = done ? 0 : tile / mn_tiles;
       if (!done) {
-        tile_coords<BN>(tile, tiles_m, tiles_n, m0, n0);
+        tile_coords<BN>(tile - q * mn_tiles, tiles_m, tiles_n, m0, n0);
         if (tile_skipped<BN>(cmode, m0, n0)) continue;
       }
-      const int nk = done ? 1 : KT;
+      const int kbeg = q * Ks;                 // 0 without split-K (Ks = 0)
+      const int nk = done ? 1 : kt_of(q);
       for (int kt = 0; kt < nk; kt++, it++) {
         const uint32_t s = it % STAGES;
         const uint32_t ph = (it / STAGES) & 1;
@@ -210,7 +217,7 @@ dgemm_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         if (kt == 0 && lane == 0) asm volatile("st.shared.s32 [%0], %1;" ::"r"(ring_base + 4 * s), "r"(done ? -1 : tile) : "memory");
         if (done) { if (lane == 0) mbar_arrive(full); break; }
         const uint32_t sa = smem_base + s * STAGE_BYTES, sb = sa + A_TILE_BYTES;
-        const int k0 = kt * BK;
+        const int k0 = kbeg + kt * BK;
         if (lane == 0) mbar_expect_tx(full, STAGE_BYTES);
         __syncwarp();
         if (A_KMAJOR) { if (lane == 0) tma_load_2d(sa, &tmA, k0, m0, full); }
@@ -246,9 +253,11 @@ dgemm_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     asm volatile("ld.shared.s32 %0, [%1];" : "=r"(tile) : "r"(ring_base + 4 * (it % STAGES)) : "memory");
     if (tile < 0) break;
     int m0, n0;
-    tile_coords<BN>(tile, tiles_m, tiles_n, m0, n0);
+    const int q = tile / mn_tiles;
+    tile_coords<BN>(tile - q * mn_tiles, tiles_m, tiles_n, m0, n0);
+    const int KT = kt_of(q);
 
-    if (!beta0) {
+    if (!beta0 && ksplit == 1) {
       // bring this tile's C block (128 columns x 1 KiB) into L2 while the k loop runs: thread i of
       // the 256 consumers takes column i/2, half i%2, four 128-byte lines
       const int ctid = (int)threadIdx.x;               // consumer warps are 0..7
@@ -321,6 +330,23 @@ dgemm_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     // fit: 3 of the 9 warps share a 16K-register sub-partition, which caps the kernel at 168
     // registers, 128 of them accumulators).  The rounds hit L2 because the C block was prefetched
     // at the start of the tile; from DRAM they cost 9.6 us per tile, 12 % of a K=512 update.
+    if (ksplit > 1) {          // partial product of slice q, as computed (alpha and beta belong to the reduction)
+      double* W = Wsplit + (size_t)q * M * N;
+#pragma unroll
+      for (int ni = 0; ni < NI; ni++) {
+#pragma unroll
+        for (int e = 0; e < 2; e++) {
+          const int n = n0 + wn * 8 * NI + ni * 8 + 2 * t + e;
+          if (n >= N) continue;
+#pragma unroll
+          for (int mi = 0; mi < 8; mi++) {
+            const int m = m0 + wm * 64 + mi * 8 + g;
+            if (m < M) W[(size_t)n * M + m] = acc[mi][ni][e];
+          }
+        }
+      }
+      continue;
+    }
     const bool interior = (cmode == C_FULL) && (m0 + BM <= M) && (n0 + BN <= N);
 #pragma unroll
     for (int ni = 0; ni < NI; ni++) {
@@ -391,15 +417,29 @@ bool make_map(CUtensorMap* tm, const double* ptr, size_t rows, size_t cols, size
 // look-ahead reservation state of the calling thread (set by set_gemm_reserved)
 thread_local SmMask g_reserved = {{0, 0, 0, 0}};
 thread_local bool g_reserved_on = false;
+thread_local bool g_splitk_ok = false;     // set by the GEMM entry points of the C ABI only (set_gemm_splitk_allowed)
 thread_local int* g_counters[AB_MAX_DEV] = {};   // ring of device tile counters, one ring per device
 thread_local int g_counter_next = 0;
 // (a counter is zeroed in stream order right before its launch and must not be reused while that launch is pending: the host
 //  runs at most ~1000 launches ahead of the device)
+// C <- alpha * (W[0] + W[1] + ... in this order) + beta * C over the M x N partial products of a split-K launch
+__global__ void __launch_bounds__(256) splitk_reduce_kernel(int M, int N, int ksplit, const double* __restrict__ W, double alpha, double beta,
+                                                             double* __restrict__ C, size_t ldc) {
+  const size_t total = (size_t)M * N;
+  for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+    double s = W[idx];
+    for (int q = 1; q < ksplit; q++) s += W[(size_t)q * total + idx];
+    const size_t n = idx / M, m = idx - n * M;
+    double* c = C + n * ldc + m;
+    *c = (beta == 0.) ? alpha * s : alpha * s + beta * *c;
+  }
+}
+
 constexpr int NCOUNTERS = 8192;
 
 template <bool AK, bool BK_, int NI>
 void launch(const CUtensorMap& ta, const CUtensorMap& tb, double* C, size_t ldc, int M, int N, int K, double alpha,
-            double beta, int cmode, const int* abort_flag) {
+            double beta, int cmode, const int* abort_flag, int ksplit = 1) {
   constexpr int smem_req = TileN<NI>::SMEM_BYTES, BN = TileN<NI>::BN;
   static PerDeviceOnce attr_once;
   attr_once([] { AB_CUDA_CHECK(cudaFuncSetAttribute(dgemm_tma_kernel<AK, BK_, NI>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_req)); });
@@ -407,6 +447,28 @@ void launch(const CUtensorMap& ta, const CUtensorMap& tb, double* C, size_t ldc,
   int grid = std::min(tiles_m * tiles_n, gemm_cta_cap());
   SmMask mask = {{0, 0, 0, 0}};
   int* counter = nullptr;
+  if (ksplit > 1) {
+    // small problem: the k range is cut into ksplit slices so that every SM has work; partial products go to a stream-ordered
+    // scratch buffer and are added in a fixed order (the reference's ammm_tN / ammm_IP special cases split long-K small-C
+    // problems the same way, atlas-ammm.base:16370 ff.)
+    const int Ks = (((K + ksplit - 1) / ksplit) + BK - 1) / BK * BK;
+    ksplit = (K + Ks - 1) / Ks;
+    double* W = nullptr;
+    cudaStream_t st = current_stream();
+    keep_pool_cached();
+    AB_CUDA_CHECK(cudaMallocAsync(reinterpret_cast<void**>(&W), sizeof(double) * (size_t)M * N * ksplit, st));
+    grid = std::min(tiles_m * tiles_n * ksplit, gemm_cta_cap());
+    dgemm_tma_kernel<AK, BK_, NI><<<grid, THREADS, smem_req, st>>>(ta, tb, C, ldc, M, N, K, 1.0, 0.0, C_FULL, tiles_m, tiles_n, abort_flag,
+                                                                   mask, counter, ksplit, Ks, W);
+    count_launch();
+    AB_CUDA_CHECK(cudaGetLastError());
+    const size_t total = (size_t)M * N;
+    splitk_reduce_kernel<<<(unsigned)std::min<size_t>((total + 255) / 256, 2048), 256, 0, st>>>(M, N, ksplit, W, alpha, beta, C, ldc);
+    count_launch();
+    AB_CUDA_CHECK(cudaGetLastError());
+    AB_CUDA_CHECK(cudaFreeAsync(W, st));
+    return;
+  }
   if ((g_reserved_on || cmode != C_FULL) && tiles_m * tiles_n > 2 * gemm_cta_cap()) {
     // one CTA per SM; the ones on reserved SMs leave, the rest share the tiles through a counter
     // (also used for SYRK: half of the tiles are skipped, a static stride would be unbalanced)
@@ -418,7 +480,7 @@ void launch(const CUtensorMap& ta, const CUtensorMap& tb, double* C, size_t ldc,
     AB_CUDA_CHECK(cudaMemsetAsync(counter, 0, sizeof(int), current_stream()));
   }
   dgemm_tma_kernel<AK, BK_, NI><<<grid, THREADS, smem_req, current_stream()>>>(
-      ta, tb, C, ldc, M, N, K, alpha, beta, cmode, tiles_m, tiles_n, abort_flag, mask, counter);
+      ta, tb, C, ldc, M, N, K, alpha, beta, cmode, tiles_m, tiles_n, abort_flag, mask, counter, 1, 0, nullptr);
   count_launch();
   AB_CUDA_CHECK(cudaGetLastError());
 }
@@ -430,6 +492,37 @@ int pick_ni(int M, int N) {
   if (forced == 128) return 4;
   const long long t128 = (long long)((M + BM - 1) / BM) * ((N + 127) / 128);
   return (t128 < gemm_cta_cap() && N > 64) ? 2 : 4;
+}
+
+// Tile width and k split for one problem (split-K is for GEMM calls that arrive through the C ABI; the small products inside
+// TRSM / LU / Cholesky run on several streams at once, where a scratch buffer from the stream-ordered pool would tie the
+// streams together - measured: DGETRF N=16384 137 -> 147 ms): minimise  rounds x (time of one work item)  +  reduction pass, with the measured
+// 244 GFLOP/s per SM, ~2 us to fill the stage ring per work item and ~3 TB/s for the reduction.  Only plain GEMMs (full C,
+// no SM reservation) are split; a split never leaves fewer than 64 k per slice.
+void pick_shape(int M, int N, int K, int cmode, int& ni, int& ksplit) {
+  ni = pick_ni(M, N);
+  ksplit = 1;
+  static const int on = [] { const char* v = getenv("ATLB200_GEMM_SPLITK"); return v ? atoi(v) : 1; }();
+  if (!on || !g_splitk_ok || cmode != C_FULL || g_reserved_on || K < 128) return;
+  const int cap = gemm_cta_cap();
+  const long long tm = (M + BM - 1) / BM;
+  if (tm * ((N + 127) / 128) >= 4LL * cap) return;         // large: the persistent schedule is already balanced
+  static const int forced = [] { const char* v = getenv("ATLB200_GEMM_BN"); return v ? atoi(v) : 0; }();
+  double best = 1e30;
+  for (int cand_ni = 2; cand_ni <= 4; cand_ni += 2) {
+    if ((forced == 64 && cand_ni != 2) || (forced == 128 && cand_ni != 4)) continue;
+    const int bn = 32 * cand_ni;
+    const long long tiles = tm * ((N + bn - 1) / bn);
+    for (int ks = 1; ks <= 16; ks *= 2) {
+      if (ks > 1 && K / ks < 64) break;
+      if (ks > 1 && (size_t)M * N * ks * 8 > (size_t)256 << 20) break;
+      const long long rounds = (tiles * ks + cap - 1) / cap;
+      const double item = 2.0 * BM * bn * ((double)K / ks) / 244e9 + 2e-6;
+      const double red = ks > 1 ? 6e-6 + (double)(ks + 2) * M * N * 8 / 3e12 : 0.0;
+      const double t = rounds * item + red;
+      if (t < best * 0.97) { best = t; ni = cand_ni; ksplit = ks; }
+    }
+  }
 }
 
 }  // namespace
@@ -446,6 +539,7 @@ int gemm_cta_cap() {
   return sms[dev];
 }
 void set_gemm_cta_cap(int cap) { g_cta_cap = cap; }
+void set_gemm_splitk_allowed(bool on) { g_splitk_ok = on; }
 void set_gemm_reserved(const unsigned long long* mask4) {
   if (mask4) { for (int i = 0; i < 4; i++) g_reserved.w[i] = mask4[i]; g_reserved_on = true; }
   else g_reserved_on = false;
@@ -465,15 +559,16 @@ bool dgemm_tma(int ta, int tb, int M, int N, int K, double alpha, const double* 
   if (!dgemm_tma_eligible(M, N, K, A, lda, B, ldb)) return false;
   CUtensorMap mA, mB;
   bool ok;
-  const int ni = pick_ni(M, N);
+  int ni, ksplit;
+  pick_shape(M, N, K, cmode, ni, ksplit);
   // op(A) is M x K.  ta: stored K x M (k contiguous, K-major) else stored M x K (m contiguous).
   ok = ta ? make_map(&mA, A, K, M, lda, BK, BM) : make_map(&mA, A, M, K, lda, 16, BK);
   if (!ok) return false;
   // op(B) is K x N.  !tb: stored K x N (K-major) else stored N x K (n contiguous).
   ok = tb ? make_map(&mB, B, N, K, ldb, 16, BK) : make_map(&mB, B, K, N, ldb, BK, 32 * ni);
   if (!ok) return false;
-#define AB_GO(AK, BKM) do { if (ni == 2) launch<AK, BKM, 2>(mA, mB, C, ldc, M, N, K, alpha, beta, cmode, abort_flag); \
-                            else launch<AK, BKM, 4>(mA, mB, C, ldc, M, N, K, alpha, beta, cmode, abort_flag); } while (0)
+#define AB_GO(AK, BKM) do { if (ni == 2) launch<AK, BKM, 2>(mA, mB, C, ldc, M, N, K, alpha, beta, cmode, abort_flag, ksplit); \
+                            else launch<AK, BKM, 4>(mA, mB, C, ldc, M, N, K, alpha, beta, cmode, abort_flag, ksplit); } while (0)
   if (ta) { if (!tb) AB_GO(true, true); else AB_GO(true, false); }
   else    { if (!tb) AB_GO(false, true); else AB_GO(false, false); }
 #undef AB_GO

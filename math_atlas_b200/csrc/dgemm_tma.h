@@ -14,5 +14,8 @@ void set_gemm_cta_cap(int cap);
 // SMs (bit i of mask4 = SM i) the calling thread's DGEMM launches must stay off, nullptr = none.
 // Used by the LU/Cholesky look-ahead so that the panel's thread-block cluster finds a free GPC.
 void set_gemm_reserved(const unsigned long long* mask4);
+// Split-K for small problems is applied only while this is on (the cblas / F77 / ATL GEMM entry points turn it on around
+// their launch); see pick_shape in dgemm_tma.cu.
+void set_gemm_splitk_allowed(bool on);
 int gemm_cta_cap();
 }  // namespace ab

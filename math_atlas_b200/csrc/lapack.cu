@@ -1042,25 +1042,13 @@ static void getrf_lookahead(int M, int N, T* A, size_t lda, int* d_ipiv, int* d_
       const int c0 = c1 + w1, nc = nright - w1;
       T* Akk = A + (size_t)k0 + (size_t)k0 * lda;
       const bool aux_step = use_aux && more && nc > 0;
-      if (more) {
-        // next panel's columns first.  Their interchanges run ALONE: R's pass over the rest columns (14 000 columns of
-        // 32-byte-sector traffic) starts behind them - side by side the narrow pass took 0.22 ms instead of 0.05 - and then
-        // shares the GPU with the next panel's solve and update, which do not compete for the same resource.
-        g_lutr.begin(PH_NEXT_SWAP);
-        laswp<T>(w1, A + (size_t)c1 * lda, lda, k0, k0 + w, d_ipiv, 1);
-        g_lutr.end();
-      }
       if (aux_step) AB_CUDA_CHECK(cudaEventRecord(ss.have[k & 1], U));
       if (more) {
-        g_lutr.begin(PH_NEXT_TRSM);
-        trsm<T>(Left, Lower, NoTrans, Unit, w, w1, S::one(), Akk, lda, A + (size_t)k0 + (size_t)c1 * lda, lda);
-        g_lutr.end();
-        if (M - k0 - w > 0) {
-          g_lutr.begin(PH_NEXT_GEMM);
-          gemm<T>(NoTrans, NoTrans, M - k0 - w, w1, w, S::from_real(-1), A + (size_t)(k0 + w) + (size_t)k0 * lda, lda,
-                  A + (size_t)k0 + (size_t)c1 * lda, lda, S::one(), A + (size_t)(k0 + w) + (size_t)c1 * lda, lda);
-          g_lutr.end();
-        }
+        // Issued BEFORE R's kernels: both are ready at the same moment and the block scheduler serves them in issue order; the
+        // next panel's columns are the critical path, the rest columns have slack.  (Holding R back until U's interchanges
+        // or its solve are through was measured too - R's 14 000-column pass then collides with the next kernel of the
+        // chain instead: 139 ms -> 159 / 146 ms, gpurun log s2_lu_exp9.)
+        lu_apply_panel<T>(A, lda, M, k0, w, c1, w1, d_ipiv, PH_NEXT_SWAP);    // next panel's columns first
         AB_CUDA_CHECK(cudaEventRecord(ss.cols[k & 1], U));
       }
       if (aux_step) {
