@@ -49,6 +49,9 @@ void her2k(int uplo, int trans, int N, int K, T alpha, const T* A, size_t lda, c
 // Row interchanges (reference ATL_laswp, Clint/atlas-lp.base:1053); piv is a DEVICE array here.
 template <typename T>
 void laswp(int N, T* A, size_t lda, int K1, int K2, const int* d_piv, int inci);
+// column block b (blk_cols wide) takes the interchanges K1 + b*k1_step .. K2-1 (one launch; multi-GPU LU, lapack.cu)
+template <typename T>
+void laswp_block_steps(int N, T* A, size_t lda, int K1, int K2, const int* d_piv, int blk_cols, int k1_step);
 
 // Column-major recursive LU with partial pivoting (reference ATL_getrfC, Clint/atlas-lp.base:1497-1617).
 // d_ipiv: device int[min(M,N)], 0-based; d_info: device int, set to the 1-based index of the first

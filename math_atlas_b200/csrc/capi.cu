@@ -382,6 +382,207 @@ static bool atl_gemm_multi(int TA, int TB, size_t M, size_t N, size_t K, T alpha
   return true;
 }
 
+// ---- clapack_Xgetrf on several GPUs from one host thread (the role of the reference's ATL_tgetrf / ATL_tgetrf_bcAmm,
+// Clint/atlas-thr.base + Students/fact-amm.base:73-1480, behind the same entry point) --------------------------------------
+// Same opt-in as the GEMM above (ATLB200_DEVICES / atlb200_set_devices).  Layout and schedule are those of
+// math_atlas_b200/dist.py (the torchrun drivers), with peer copies in place of NCCL since one process sees every device:
+//   * block-cyclic column panels of NB = 512 over a 1 x D grid (index maps IDXG2P / NUMROC of ATL_getrf_bcAmm.c:57-90); the
+//     latency-bound panel stays whole on its owner, interchanges never cross devices;
+//   * step k: the owner factors panel k (on a high-priority side stream when the cluster leaf can run beside its update
+//     GEMM), every other device PULLS panel + pivots over NVLink on its own copy stream (D-1 concurrent pulls, receive
+//     buffers double-buffered), then each device applies the interchanges, the U-block solve and the Schur-complement
+//     GEMM to its trailing columns - the owner of panel k+1 its next block first (look-ahead 1);
+//   * the interchanges LEFT of the panels are applied at the end, one launch per device (laswp_block_steps).
+namespace {
+__global__ void piv_abs_kernel(int n, int nb, const int* rel, int* abs_) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) abs_[i] = rel[i] + (i / nb) * nb;
+}
+struct LuDev {
+  cudaStream_t main = nullptr, side = nullptr, recv = nullptr;
+  cudaEvent_t factored[2] = {nullptr, nullptr}, arrived[2] = {nullptr, nullptr}, upd_done[2] = {nullptr, nullptr}, cols = nullptr;
+};
+LuDev g_ludev[AB_MAX_DEV];
+}  // namespace
+
+template <typename T>
+static bool atl_getrf_multi(int M, int N, T* A, size_t lda, int* ipiv, int* info_out) {
+  const int D = multi_devices();
+  if (D <= 1 || g_async) return false;
+  if (is_device_ptr(A) || is_device_ptr(ipiv)) return false;
+  constexpr int NB = 512;
+  const int MN = std::min(M, N);
+  if (MN < 8 * NB || N < 2 * NB * D) return false;
+  std::lock_guard<std::mutex> lock(g_multi_mu);
+  using S = ST<T>;
+  const size_t esz = sizeof(T);
+  int home = 0;
+  AB_CUDA_CHECK(cudaGetDevice(&home));
+  cudaStream_t home_stream = current_stream();
+  const int nblk = (N + NB - 1) / NB, nsteps = (MN + NB - 1) / NB;
+  const size_t ld = ((size_t)M + 15) & ~(size_t)15;
+  auto owner = [&](int k) { return k % D; };
+  auto width = [&](int k) { return std::min(NB, N - k * NB); };
+  auto lcol = [&](int k) { return (k / D) * NB; };                    // local column of block k on its owner (all earlier blocks are full)
+  auto first_local_block_after = [&](int d, int k) { int b = k + 1; while (b % D != d) b++; return b; };   // first block > k owned by d
+  std::vector<int> ncl(D, 0);
+  for (int k = 0; k < nblk; k++) ncl[owner(k)] += width(k);
+  std::vector<T*> Aloc(D, nullptr);
+  std::vector<T*> pbuf(2 * D, nullptr);
+  std::vector<int*> prel(D, nullptr), pabs(D, nullptr), dinfo(D, nullptr);
+  int* hpin = nullptr;                                              // pinned: MN relative pivots + nsteps info words
+  AB_CUDA_CHECK(cudaMallocHost(&hpin, sizeof(int) * ((size_t)MN + nsteps)));
+  for (int d = 0; d < D; d++) {
+    AB_CUDA_CHECK(cudaSetDevice(d));
+    LuDev& x = g_ludev[d];
+    if (!x.main) {
+      int lo = 0, hi = 0;
+      AB_CUDA_CHECK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+      AB_CUDA_CHECK(cudaStreamCreateWithFlags(&x.main, cudaStreamNonBlocking));
+      AB_CUDA_CHECK(cudaStreamCreateWithPriority(&x.side, cudaStreamNonBlocking, hi));
+      AB_CUDA_CHECK(cudaStreamCreateWithFlags(&x.recv, cudaStreamNonBlocking));
+      for (int i = 0; i < 2; i++) {
+        AB_CUDA_CHECK(cudaEventCreateWithFlags(&x.factored[i], cudaEventDisableTiming));
+        AB_CUDA_CHECK(cudaEventCreateWithFlags(&x.arrived[i], cudaEventDisableTiming));
+        AB_CUDA_CHECK(cudaEventCreateWithFlags(&x.upd_done[i], cudaEventDisableTiming));
+      }
+      AB_CUDA_CHECK(cudaEventCreateWithFlags(&x.cols, cudaEventDisableTiming));
+    }
+    DevCtx& cx = g_dev[d];
+    if (!cx.peers) {
+      for (int p = 0; p < D; p++)
+        if (p != d) { int can = 0; cudaDeviceCanAccessPeer(&can, d, p); if (can && cudaDeviceEnablePeerAccess(p, 0) != cudaSuccess) (void)cudaGetLastError(); }
+      cx.peers = true;
+    }
+    keep_pool_cached();
+    AB_CUDA_CHECK(cudaMallocAsync(&Aloc[d], esz * ld * std::max(ncl[d], 1), x.main));
+    for (int i = 0; i < 2; i++) AB_CUDA_CHECK(cudaMallocAsync(&pbuf[2 * d + i], esz * ld * NB, x.main));
+    AB_CUDA_CHECK(cudaMallocAsync(&prel[d], sizeof(int) * (size_t)MN, x.main));
+    AB_CUDA_CHECK(cudaMallocAsync(&pabs[d], sizeof(int) * (size_t)MN, x.main));
+    AB_CUDA_CHECK(cudaMallocAsync(&dinfo[d], sizeof(int) * (size_t)nsteps, x.main));
+    for (int k = d; k < nblk; k += D)                                // this device's column blocks
+      AB_CUDA_CHECK(cudaMemcpy2DAsync(Aloc[d] + (size_t)lcol(k) * ld, esz * ld, A + (size_t)k * NB * lda, esz * lda, esz * M, width(k),
+                                      cudaMemcpyHostToDevice, x.main));
+  }
+  // panel k as device d sees it: the owner reads it in place, the others from their receive buffer
+  auto panel_ptr = [&](int d, int k) { return d == owner(k) ? Aloc[d] + (size_t)k * NB + (size_t)lcol(k) * ld : pbuf[2 * d + (k & 1)]; };
+  auto geom = [&](int k, int& k0, int& wc, int& w, int& Mk) { k0 = k * NB; wc = width(k); w = std::min(wc, MN - k0); Mk = M - k0; };
+  // factor panel k on its owner (stream st) and let the other devices pull it
+  auto post = [&](int k, cudaStream_t st) {
+    int k0, wc, w, Mk; geom(k, k0, wc, w, Mk);
+    const int o = owner(k);
+    AB_CUDA_CHECK(cudaSetDevice(o));
+    set_current_stream(st);
+    getrf<T>(Mk, wc, panel_ptr(o, k), ld, prel[o] + k0, dinfo[o] + k);
+    AB_CUDA_CHECK(cudaMemcpyAsync(hpin + k0, prel[o] + k0, sizeof(int) * (size_t)w, cudaMemcpyDeviceToHost, st));
+    AB_CUDA_CHECK(cudaMemcpyAsync(hpin + MN + k, dinfo[o] + k, sizeof(int), cudaMemcpyDeviceToHost, st));
+    AB_CUDA_CHECK(cudaEventRecord(g_ludev[o].factored[k & 1], st));
+    for (int d = 0; d < D; d++) {
+      if (d == o) continue;
+      AB_CUDA_CHECK(cudaSetDevice(d));
+      LuDev& x = g_ludev[d];
+      AB_CUDA_CHECK(cudaStreamWaitEvent(x.recv, g_ludev[o].factored[k & 1], 0));
+      if (k >= 2) AB_CUDA_CHECK(cudaStreamWaitEvent(x.recv, x.upd_done[k & 1], 0));      // the buffer's previous panel has been consumed
+      {   // Mk x wc panel, pitch ld on both sides (an explicit peer copy: stream-ordered pool memory is not mapped into peers)
+        cudaMemcpy3DPeerParms pp{};
+        pp.srcDevice = o; pp.dstDevice = d;
+        pp.srcPtr = make_cudaPitchedPtr(const_cast<T*>(panel_ptr(o, k)), esz * ld, esz * Mk, wc);
+        pp.dstPtr = make_cudaPitchedPtr(pbuf[2 * d + (k & 1)], esz * ld, esz * Mk, wc);
+        pp.extent = make_cudaExtent(esz * Mk, wc, 1);
+        AB_CUDA_CHECK(cudaMemcpy3DPeerAsync(&pp, x.recv));
+      }
+      AB_CUDA_CHECK(cudaMemcpyPeerAsync(prel[d] + k0, d, prel[o] + k0, o, sizeof(int) * (size_t)w, x.recv));
+      AB_CUDA_CHECK(cudaEventRecord(x.arrived[k & 1], x.recv));
+    }
+  };
+  // apply panel k to local columns [c0, c1) of device d (current device, current stream set by the caller)
+  auto update = [&](int d, int k, int c0, int c1) {
+    int k0, wc, w, Mk; geom(k, k0, wc, w, Mk);
+    const int nc = c1 - c0;
+    if (nc <= 0) return;
+    const T* P = panel_ptr(d, k);
+    T* B = Aloc[d] + (size_t)k0 + (size_t)c0 * ld;
+    laswp<T>(nc, B, ld, 0, w, prel[d] + k0, 1);
+    trsm<T>(Left, Lower, NoTrans, Unit, w, nc, S::one(), P, ld, B, ld);
+    if (Mk > w) gemm<T>(NoTrans, NoTrans, Mk - w, nc, w, S::from_real(-1), P + w, ld, B, ld, S::one(), B + w, ld);
+  };
+  const char pre = std::is_same<T, float>::value ? 's' : std::is_same<T, double>::value ? 'd' : std::is_same<T, float2>::value ? 'c' : 'z';
+  post(0, g_ludev[owner(0)].main);
+  for (int k = 0; k < nsteps; k++) {
+    const bool nxt = k + 1 < nsteps;
+    const int o1 = nxt ? owner(k + 1) : -1;
+    for (int d = 0; d < D; d++) {
+      AB_CUDA_CHECK(cudaSetDevice(d));
+      LuDev& x = g_ludev[d];
+      set_current_stream(x.main);
+      AB_CUDA_CHECK(cudaStreamWaitEvent(x.main, d == owner(k) ? x.factored[k & 1] : x.arrived[k & 1], 0));
+      const int fb = first_local_block_after(d, k);
+      const int t0 = fb < nblk ? lcol(fb) : ncl[d];                    // my trailing columns start here
+      if (d == o1) {
+        const int w1 = width(k + 1);
+        update(d, k, t0, t0 + w1);                                       // bring the next panel up to date first ...
+        const bool use_side = lu_panel_overlaps(pre, M - (k + 1) * NB) != 0;
+        if (use_side) {
+          AB_CUDA_CHECK(cudaEventRecord(x.cols, x.main));
+          AB_CUDA_CHECK(cudaStreamWaitEvent(x.side, x.cols, 0));
+          post(k + 1, x.side);                                           // ... factor it beside the rest of the update
+          AB_CUDA_CHECK(cudaSetDevice(d));
+          set_current_stream(x.main);
+          lu_reserve_sms(16);
+        } else {
+          post(k + 1, x.main);
+          AB_CUDA_CHECK(cudaSetDevice(d));
+          set_current_stream(x.main);
+        }
+        update(d, k, t0 + w1, ncl[d]);
+        lu_reserve_sms(0);
+      } else
+        update(d, k, t0, ncl[d]);
+      AB_CUDA_CHECK(cudaEventRecord(x.upd_done[k & 1], x.main));
+    }
+  }
+  // everything factored; nobody pulls from anybody any more once all streams have drained
+  for (int d = 0; d < D; d++) {
+    AB_CUDA_CHECK(cudaSetDevice(d));
+    AB_CUDA_CHECK(cudaStreamSynchronize(g_ludev[d].recv));
+    AB_CUDA_CHECK(cudaStreamSynchronize(g_ludev[d].side));
+    AB_CUDA_CHECK(cudaStreamSynchronize(g_ludev[d].main));
+  }
+  for (int d = 0; d < D; d++) {
+    AB_CUDA_CHECK(cudaSetDevice(d));
+    LuDev& x = g_ludev[d];
+    set_current_stream(x.main);
+    // a device that was never the receiver of a panel it owns holds that panel's pivots already (prel is written by getrf)
+    piv_abs_kernel<<<(MN + 255) / 256, 256, 0, x.main>>>(MN, NB, prel[d], pabs[d]);
+    // interchanges left of the panels: local block j (global d + j*D) takes pivots (d + j*D + 1)*NB .. MN-1
+    laswp_block_steps<T>(ncl[d], Aloc[d], ld, (d + 1) * NB, MN, pabs[d], NB, D * NB);
+    for (int k = d; k < nblk; k += D)
+      AB_CUDA_CHECK(cudaMemcpy2DAsync(A + (size_t)k * NB * lda, esz * lda, Aloc[d] + (size_t)lcol(k) * ld, esz * ld, esz * M, width(k),
+                                      cudaMemcpyDeviceToHost, x.main));
+  }
+  for (int d = 0; d < D; d++) {
+    AB_CUDA_CHECK(cudaSetDevice(d));
+    LuDev& x = g_ludev[d];
+    AB_CUDA_CHECK(cudaStreamSynchronize(x.main));
+    AB_CUDA_CHECK(cudaFreeAsync(Aloc[d], x.main));
+    for (int i = 0; i < 2; i++) AB_CUDA_CHECK(cudaFreeAsync(pbuf[2 * d + i], x.main));
+    AB_CUDA_CHECK(cudaFreeAsync(prel[d], x.main));
+    AB_CUDA_CHECK(cudaFreeAsync(pabs[d], x.main));
+    AB_CUDA_CHECK(cudaFreeAsync(dinfo[d], x.main));
+  }
+  int info = 0;
+  for (int k = 0; k < nsteps; k++) {
+    const int k0 = k * NB, w = std::min(width(k), MN - k0);
+    for (int i = 0; i < w; i++) ipiv[k0 + i] = hpin[k0 + i] + k0;
+    if (!info && hpin[MN + k]) info = hpin[MN + k] + k0;
+  }
+  AB_CUDA_CHECK(cudaFreeHost(hpin));
+  AB_CUDA_CHECK(cudaSetDevice(home));
+  set_current_stream(home_stream);
+  *info_out = info;
+  return true;
+}
+
 template <typename T>
 static void atl_gemm(int TA, int TB, size_t M, size_t N, size_t K, T alpha, const T* A, size_t lda, const T* B, size_t ldb,
                      T beta, T* C, size_t ldc) {
@@ -452,9 +653,10 @@ static int atl_getrf(int order, int M, int N, T* A, int lda, int* ipiv) {
   const int rows = (order == ColMajor) ? M : N, cols = (order == ColMajor) ? N : M;
   const int MN = M < N ? M : N;
   if (MN <= 0) return 0;
+  int h_info = 0;
+  if (atl_getrf_multi<T>(rows, cols, A, (size_t)lda, ipiv, &h_info)) return h_info;
   Operand<T> a(A, rows, cols, (size_t)lda, true, true);
   DevInts piv(ipiv, MN, false);
-  int h_info = 0;
   DevInts info(&h_info, 1, false);
   getrf<T>(rows, cols, a.d, a.ld, piv.d, info.d);
   a.finish(); piv.finish(true); info.finish(true);

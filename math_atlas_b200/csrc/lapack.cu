@@ -150,11 +150,15 @@ __global__ void __launch_bounds__(64) laswp_kernel(int N, T* A, size_t lda, int 
 // handled by the composition itself), then all gathers of the batch are issued, then all stores.  The composition of batch
 // j+1 overlaps the loads of batch j.  512 pivots x 512 columns: 0.42 ms -> ~0.05 ms.
 template <typename T, int TPC>
-__global__ void __launch_bounds__(64) laswp_par_kernel(int N, T* A, size_t lda, int K1, int K2, const int* piv) {
+__global__ void __launch_bounds__(64) laswp_par_kernel(int N, T* A, size_t lda, int K1, int K2, const int* piv, int blk_cols, int blk_k1_step) {
   constexpr int CPW = 32 / TPC;            // columns per warp
   constexpr int EPT = 32 / TPC;            // top (and displaced) entries per thread
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const int col = (blockIdx.x * 2 + wid) * CPW + lane / TPC;
+  // blk_cols > 0 (a multiple of the columns per warp): column block b = col / blk_cols starts at pivot K1 + b * blk_k1_step -
+  // the interchanges "left of the panels" of a whole blocked factorisation applied in one launch (multi-GPU LU)
+  if (blk_cols > 0) K1 += (((blockIdx.x * 2 + wid) * CPW) / blk_cols) * blk_k1_step;
+  if (K1 >= K2) return;
   const int q = lane % TPC;
   const bool live = col < N;
   T* bp = A + (size_t)(live ? col : 0) * lda;
@@ -220,8 +224,8 @@ static void laswp_blocks(int N, T* A, size_t lda, int K1, int K2, const int* d_p
   static const int par = env_int("ATLB200_LASWP_PAR", 1);
   if (par && inci == 1 && k1_step == 0 && K2 - K1 >= 8) {
     // narrow column sets: 16 threads per column (more CTAs); wide ones: 8 threads per column
-    if (N <= 4096) laswp_par_kernel<T, 16><<<(N + 3) / 4, 64, 0, current_stream()>>>(N, A, lda, K1, K2, d_piv);
-    else laswp_par_kernel<T, 8><<<(N + 7) / 8, 64, 0, current_stream()>>>(N, A, lda, K1, K2, d_piv);
+    if (N <= 4096) laswp_par_kernel<T, 16><<<(N + 3) / 4, 64, 0, current_stream()>>>(N, A, lda, K1, K2, d_piv, 0, 0);
+    else laswp_par_kernel<T, 8><<<(N + 7) / 8, 64, 0, current_stream()>>>(N, A, lda, K1, K2, d_piv, 0, 0);
     count_launch();
     AB_CUDA_CHECK(cudaGetLastError());
     return;
@@ -233,6 +237,20 @@ static void laswp_blocks(int N, T* A, size_t lda, int K1, int K2, const int* d_p
 }
 template <typename T>
 void laswp(int N, T* A, size_t lda, int K1, int K2, const int* d_piv, int inci) { laswp_blocks<T>(N, A, lda, K1, K2, d_piv, inci, 0); }
+
+// Column block b (blk_cols columns, blk_cols % 8 == 0) of the N columns at A receives the interchanges K1 + b*k1_step .. K2-1
+// (absolute row indices in d_piv): what is left to do, at the end of a block-cyclic LU, on the blocks a device owns.
+template <typename T>
+void laswp_block_steps(int N, T* A, size_t lda, int K1, int K2, const int* d_piv, int blk_cols, int k1_step) {
+  if (N <= 0 || K2 <= K1) return;
+  laswp_par_kernel<T, 8><<<(N + 7) / 8, 64, 0, current_stream()>>>(N, A, lda, K1, K2, d_piv, blk_cols, k1_step);
+  count_launch();
+  AB_CUDA_CHECK(cudaGetLastError());
+}
+template void laswp_block_steps<float>(int, float*, size_t, int, int, const int*, int, int);
+template void laswp_block_steps<double>(int, double*, size_t, int, int, const int*, int, int);
+template void laswp_block_steps<float2>(int, float2*, size_t, int, int, const int*, int, int);
+template void laswp_block_steps<double2>(int, double2*, size_t, int, int, const int*, int, int);
 
 // ------------------------------------------------------------------------------------- fused interchange + unit-lower solve
 // One step of the right-looking panel factorisation (see getrf_panel below): after the leaf has factored the

@@ -83,3 +83,40 @@ dist.destroy_process_group()
     r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
                         "--master-port", "29617", path], capture_output=True, text=True, timeout=900)
     assert r.returncode == 0 and "pgetrf ok" in r.stdout, r.stdout[-3000:] + r.stderr[-3000:]
+
+
+@pytest.mark.parametrize("M,N,lda_pad", [(8192, 8192, 0), (6144, 5120, 3), (5000, 6656, 1)])
+def test_host_pointer_dgetrf_over_two_devices(M, N, lda_pad):
+    """clapack_dgetrf with host pointers and atlb200_set_devices(2): block-cyclic LU over both devices from one host thread
+    (capi.cu: atl_getrf_multi) - same pivots and factors as the single-device factorisation, tester residual, lda gap kept."""
+    if _ndev() < 2:
+        pytest.skip("needs two visible GPUs")
+    code = r"""
+import numpy as np, sys, os, time
+sys.path.insert(0, %r)
+import math_atlas_b200 as ab
+from oracle import orc
+M, N, lda = %d, %d, %d
+rng = np.random.default_rng(5)
+A0 = np.asfortranarray(rng.random((lda, N)) - 0.5)
+one = A0.copy(order="F"); two = A0.copy(order="F")
+mn = min(M, N)
+p1 = np.zeros(mn, dtype=np.int32); p2 = np.zeros(mn, dtype=np.int32)
+assert ab.clapack_dgetrf(102, M, N, one, lda, p1) == 0                          # one device
+ab.lib().atlb200_set_devices(2)
+for rep in range(2):
+    two[:] = A0
+    t0 = time.perf_counter()
+    assert ab.clapack_dgetrf(102, M, N, two, lda, p2) == 0                      # two devices
+    dt = time.perf_counter() - t0
+assert np.array_equal(p1, p2), "pivots differ between 1 and 2 devices"
+assert np.array_equal(two[M:], A0[M:]), "lda gap overwritten"
+err = np.max(np.abs(one[:M] - two[:M]))
+assert err < 1e-9, err
+if M == N:
+    r = orc.lu_resid("d", M, N, A0[:M].copy(order="F"), two[:M].copy(order="F"), p2)
+    assert r < 10.0, r
+print("multi getrf ok", err, dt)
+""" % (ROOT, M, N, M + lda_pad)
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=1200)
+    assert r.returncode == 0 and "multi getrf ok" in r.stdout, r.stdout + r.stderr
