@@ -405,6 +405,14 @@ struct LuDev {
 LuDev g_ludev[AB_MAX_DEV];
 }  // namespace
 
+static void multi_enable_peers(int d, int D) {      // current device = d
+  DevCtx& cx = g_dev[d];
+  if (cx.peers) return;
+  for (int p = 0; p < D; p++)
+    if (p != d) { int can = 0; cudaDeviceCanAccessPeer(&can, d, p); if (can && cudaDeviceEnablePeerAccess(p, 0) != cudaSuccess) (void)cudaGetLastError(); }
+  cx.peers = true;
+}
+
 template <typename T>
 static bool atl_getrf_multi(int M, int N, T* A, size_t lda, int* ipiv, int* info_out) {
   const int D = multi_devices();
@@ -448,12 +456,7 @@ static bool atl_getrf_multi(int M, int N, T* A, size_t lda, int* ipiv, int* info
       }
       AB_CUDA_CHECK(cudaEventCreateWithFlags(&x.cols, cudaEventDisableTiming));
     }
-    DevCtx& cx = g_dev[d];
-    if (!cx.peers) {
-      for (int p = 0; p < D; p++)
-        if (p != d) { int can = 0; cudaDeviceCanAccessPeer(&can, d, p); if (can && cudaDeviceEnablePeerAccess(p, 0) != cudaSuccess) (void)cudaGetLastError(); }
-      cx.peers = true;
-    }
+    multi_enable_peers(d, D);
     keep_pool_cached();
     AB_CUDA_CHECK(cudaMallocAsync(&Aloc[d], esz * ld * std::max(ncl[d], 1), x.main));
     for (int i = 0; i < 2; i++) AB_CUDA_CHECK(cudaMallocAsync(&pbuf[2 * d + i], esz * ld * NB, x.main));
@@ -583,6 +586,154 @@ static bool atl_getrf_multi(int M, int N, T* A, size_t lda, int* ipiv, int* info
   return true;
 }
 
+// ---- clapack_Xpotrf (Lower) on several GPUs from one host thread: same layout and plumbing as atl_getrf_multi; per step the
+// owner factors the diagonal block and solves the panel below it, the others pull the panel, every device updates the
+// blocks it owns (SYRK on the diagonal block, GEMM below it), the owner of block k+1 that block first (look-ahead 1;
+// math_atlas_b200/dist.py: ppotrf).  As there, the updates after a failing block are not suppressed; info is the first
+// non-positive pivot.
+template <typename T>
+static bool atl_potrf_multi(int uplo, int N, T* A, size_t lda, int* info_out) {
+  const int D = multi_devices();
+  if (D <= 1 || g_async || uplo != Lower) return false;
+  if (is_device_ptr(A)) return false;
+  constexpr int NB = 512;
+  if (N < 8 * NB || N < 2 * NB * D) return false;
+  std::lock_guard<std::mutex> lock(g_multi_mu);
+  using S = ST<T>;
+  using R = typename S::real;
+  const size_t esz = sizeof(T);
+  const int tr = S::cplx ? ConjTrans : TransT;
+  int home = 0;
+  AB_CUDA_CHECK(cudaGetDevice(&home));
+  cudaStream_t home_stream = current_stream();
+  const int nblk = (N + NB - 1) / NB;
+  const size_t ld = ((size_t)N + 15) & ~(size_t)15;
+  auto owner = [&](int k) { return k % D; };
+  auto width = [&](int k) { return std::min(NB, N - k * NB); };
+  auto lcol = [&](int k) { return (k / D) * NB; };
+  std::vector<int> ncl(D, 0);
+  for (int k = 0; k < nblk; k++) ncl[owner(k)] += width(k);
+  std::vector<T*> Aloc(D, nullptr), pbuf(2 * D, nullptr);
+  std::vector<int*> dinfo(D, nullptr);
+  int* hpin = nullptr;
+  AB_CUDA_CHECK(cudaMallocHost(&hpin, sizeof(int) * (size_t)nblk));
+  for (int d = 0; d < D; d++) {
+    AB_CUDA_CHECK(cudaSetDevice(d));
+    LuDev& x = g_ludev[d];
+    if (!x.main) {
+      int lo = 0, hi = 0;
+      AB_CUDA_CHECK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+      AB_CUDA_CHECK(cudaStreamCreateWithFlags(&x.main, cudaStreamNonBlocking));
+      AB_CUDA_CHECK(cudaStreamCreateWithPriority(&x.side, cudaStreamNonBlocking, hi));
+      AB_CUDA_CHECK(cudaStreamCreateWithFlags(&x.recv, cudaStreamNonBlocking));
+      for (int i = 0; i < 2; i++) {
+        AB_CUDA_CHECK(cudaEventCreateWithFlags(&x.factored[i], cudaEventDisableTiming));
+        AB_CUDA_CHECK(cudaEventCreateWithFlags(&x.arrived[i], cudaEventDisableTiming));
+        AB_CUDA_CHECK(cudaEventCreateWithFlags(&x.upd_done[i], cudaEventDisableTiming));
+      }
+      AB_CUDA_CHECK(cudaEventCreateWithFlags(&x.cols, cudaEventDisableTiming));
+    }
+    multi_enable_peers(d, D);
+    keep_pool_cached();
+    AB_CUDA_CHECK(cudaMallocAsync(&Aloc[d], esz * ld * std::max(ncl[d], 1), x.main));
+    for (int i = 0; i < 2; i++) AB_CUDA_CHECK(cudaMallocAsync(&pbuf[2 * d + i], esz * ld * NB, x.main));
+    AB_CUDA_CHECK(cudaMallocAsync(&dinfo[d], sizeof(int) * (size_t)nblk, x.main));
+    AB_CUDA_CHECK(cudaMemsetAsync(dinfo[d], 0, sizeof(int) * (size_t)nblk, x.main));
+    for (int k = d; k < nblk; k += D)
+      AB_CUDA_CHECK(cudaMemcpy2DAsync(Aloc[d] + (size_t)lcol(k) * ld, esz * ld, A + (size_t)k * NB * lda, esz * lda, esz * N, width(k),
+                                      cudaMemcpyHostToDevice, x.main));
+  }
+  // panel k (rows k0 .. N-1, w columns) as device d sees it
+  auto panel_ptr = [&](int d, int k) { return d == owner(k) ? Aloc[d] + (size_t)k * NB + (size_t)lcol(k) * ld : pbuf[2 * d + (k & 1)]; };
+  auto post = [&](int k, cudaStream_t st) {
+    const int k0 = k * NB, w = width(k), Mk = N - k0, o = owner(k);
+    AB_CUDA_CHECK(cudaSetDevice(o));
+    set_current_stream(st);
+    T* Akk = panel_ptr(o, k);
+    potrf<T>(Lower, w, Akk, ld, dinfo[o] + k);
+    if (Mk > w) trsm<T>(Right, Lower, tr, NonUnit, Mk - w, w, S::one(), Akk, ld, Akk + w, ld);
+    AB_CUDA_CHECK(cudaMemcpyAsync(hpin + k, dinfo[o] + k, sizeof(int), cudaMemcpyDeviceToHost, st));
+    AB_CUDA_CHECK(cudaEventRecord(g_ludev[o].factored[k & 1], st));
+    if (Mk <= w) return;
+    for (int d = 0; d < D; d++) {
+      if (d == o) continue;
+      AB_CUDA_CHECK(cudaSetDevice(d));
+      LuDev& x = g_ludev[d];
+      AB_CUDA_CHECK(cudaStreamWaitEvent(x.recv, g_ludev[o].factored[k & 1], 0));
+      if (k >= 2) AB_CUDA_CHECK(cudaStreamWaitEvent(x.recv, x.upd_done[k & 1], 0));
+      cudaMemcpy3DPeerParms pp{};
+      pp.srcDevice = o; pp.dstDevice = d;
+      pp.srcPtr = make_cudaPitchedPtr(Akk, esz * ld, esz * Mk, w);
+      pp.dstPtr = make_cudaPitchedPtr(pbuf[2 * d + (k & 1)], esz * ld, esz * Mk, w);
+      pp.extent = make_cudaExtent(esz * Mk, w, 1);
+      AB_CUDA_CHECK(cudaMemcpy3DPeerAsync(&pp, x.recv));
+      AB_CUDA_CHECK(cudaEventRecord(x.arrived[k & 1], x.recv));
+    }
+  };
+  auto update_block = [&](int d, int k, int j) {       // block j (owned by d) receives panel k
+    const int k0 = k * NB, w = width(k), j0 = j * NB, wj = width(j), off = j0 - k0;
+    const T* P = panel_ptr(d, k);
+    T* Cjj = Aloc[d] + (size_t)j0 + (size_t)lcol(j) * ld;
+    if constexpr (S::cplx) herk<T>(Lower, NoTrans, wj, w, (R)-1, P + off, ld, (R)1, Cjj, ld);
+    else syrk<T>(Lower, NoTrans, wj, w, S::from_real(-1), P + off, ld, S::one(), Cjj, ld);
+    const int rest = N - j0 - wj;
+    if (rest > 0) gemm<T>(NoTrans, tr, rest, wj, w, S::from_real(-1), P + off + wj, ld, P + off, ld, S::one(), Cjj + wj, ld);
+  };
+  post(0, g_ludev[owner(0)].main);
+  for (int k = 0; k + 1 < nblk; k++) {
+    const int o1 = owner(k + 1);
+    for (int d = 0; d < D; d++) {
+      AB_CUDA_CHECK(cudaSetDevice(d));
+      LuDev& x = g_ludev[d];
+      set_current_stream(x.main);
+      AB_CUDA_CHECK(cudaStreamWaitEvent(x.main, d == owner(k) ? x.factored[k & 1] : x.arrived[k & 1], 0));
+      int jfirst = k + 1;
+      while (jfirst % D != d) jfirst++;
+      if (d == o1) {
+        update_block(d, k, k + 1);
+        AB_CUDA_CHECK(cudaEventRecord(x.cols, x.main));
+        AB_CUDA_CHECK(cudaStreamWaitEvent(x.side, x.cols, 0));
+        post(k + 1, x.side);                          // the diagonal-block chain needs a handful of SMs only
+        AB_CUDA_CHECK(cudaSetDevice(d));
+        set_current_stream(x.main);
+        lu_reserve_sms(8);
+        jfirst += D;
+      }
+      for (int j = jfirst; j < nblk; j += D) update_block(d, k, j);
+      if (d == o1) lu_reserve_sms(0);
+      AB_CUDA_CHECK(cudaEventRecord(x.upd_done[k & 1], x.main));
+    }
+  }
+  for (int d = 0; d < D; d++) {
+    AB_CUDA_CHECK(cudaSetDevice(d));
+    AB_CUDA_CHECK(cudaStreamSynchronize(g_ludev[d].recv));
+    AB_CUDA_CHECK(cudaStreamSynchronize(g_ludev[d].side));
+    AB_CUDA_CHECK(cudaStreamSynchronize(g_ludev[d].main));
+  }
+  for (int d = 0; d < D; d++) {
+    AB_CUDA_CHECK(cudaSetDevice(d));
+    LuDev& x = g_ludev[d];
+    for (int k = d; k < nblk; k += D)
+      AB_CUDA_CHECK(cudaMemcpy2DAsync(A + (size_t)k * NB * lda, esz * lda, Aloc[d] + (size_t)lcol(k) * ld, esz * ld, esz * N, width(k),
+                                      cudaMemcpyDeviceToHost, x.main));
+  }
+  for (int d = 0; d < D; d++) {
+    AB_CUDA_CHECK(cudaSetDevice(d));
+    LuDev& x = g_ludev[d];
+    AB_CUDA_CHECK(cudaStreamSynchronize(x.main));
+    AB_CUDA_CHECK(cudaFreeAsync(Aloc[d], x.main));
+    for (int i = 0; i < 2; i++) AB_CUDA_CHECK(cudaFreeAsync(pbuf[2 * d + i], x.main));
+    AB_CUDA_CHECK(cudaFreeAsync(dinfo[d], x.main));
+  }
+  int info = 0;
+  for (int k = 0; k < nblk && !info; k++) if (hpin[k]) info = hpin[k] + k * NB;
+  AB_CUDA_CHECK(cudaFreeHost(hpin));
+  AB_CUDA_CHECK(cudaSetDevice(home));
+  set_current_stream(home_stream);
+  *info_out = info;
+  return true;
+}
+
 template <typename T>
 static void atl_gemm(int TA, int TB, size_t M, size_t N, size_t K, T alpha, const T* A, size_t lda, const T* B, size_t ldb,
                      T beta, T* C, size_t ldc) {
@@ -670,8 +821,9 @@ static int atl_potrf(int order, int uplo, int N, T* A, int lda) {
   // RowMajor: the same memory viewed column-major holds the other triangle (conjugated for
   // complex, still Hermitian positive definite), reference atlas-lp.base:336-373
   const int ul = (order == ColMajor) ? uplo : (uplo == Upper ? Lower : Upper);
-  Operand<T> a(A, N, N, (size_t)lda, true, true);
   int h_info = 0;
+  if (atl_potrf_multi<T>(ul, N, A, (size_t)lda, &h_info)) return h_info;
+  Operand<T> a(A, N, N, (size_t)lda, true, true);
   DevInts info(&h_info, 1, false);
   potrf<T>(ul, N, a.d, a.ld, info.d);
   a.finish(); info.finish(true);

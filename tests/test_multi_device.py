@@ -120,3 +120,36 @@ print("multi getrf ok", err, dt)
 """ % (ROOT, M, N, M + lda_pad)
     r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=1200)
     assert r.returncode == 0 and "multi getrf ok" in r.stdout, r.stdout + r.stderr
+
+
+@pytest.mark.parametrize("N,order,uplo", [(8192, 102, 122), (5000, 101, 121)])
+def test_host_pointer_dpotrf_over_two_devices(N, order, uplo):
+    """clapack_dpotrf (the Lower triangle of the column-major view) with host pointers on two devices (capi.cu: atl_potrf_multi)
+    against the single-device factor and the tester's residual ||A - L L^T|| / (||A|| N eps)."""
+    if _ndev() < 2:
+        pytest.skip("needs two visible GPUs")
+    code = r"""
+import numpy as np, sys
+sys.path.insert(0, %r)
+import math_atlas_b200 as ab
+N, order, uplo = %d, %d, %d
+rng = np.random.default_rng(9)
+B = rng.random((N, N)) - 0.5
+S0 = np.asfortranarray(B @ B.T / N + np.eye(N) * 2.0)
+one = S0.copy(order="F"); two = S0.copy(order="F")
+assert ab.clapack_dpotrf(order, uplo, N, one, N) == 0
+ab.lib().atlb200_set_devices(2)
+assert ab.clapack_dpotrf(order, uplo, N, two, N) == 0
+L1 = np.tril(one); L2 = np.tril(two)
+assert np.array_equal(np.triu(two, 1), np.triu(S0, 1)), "the other triangle was touched"
+err = np.max(np.abs(L1 - L2))
+assert err < 1e-10, err
+res = np.abs(L2 @ L2.T - S0).sum(axis=0).max() / (np.abs(S0).sum(axis=0).max() * N * np.finfo(np.float64).eps)
+assert res < 10.0, res
+# not positive definite: info = index of the first failing pivot, as on one device
+bad = S0.copy(order="F"); bad[3000, 3000] = -1.0
+assert ab.clapack_dpotrf(order, uplo, N, bad, N) == 3001
+print("multi potrf ok", err, res)
+""" % (ROOT, N, order, uplo)
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=1200)
+    assert r.returncode == 0 and "multi potrf ok" in r.stdout, r.stdout + r.stderr
