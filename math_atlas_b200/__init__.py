@@ -159,6 +159,13 @@ def ATL_gemm(p, TA, TB, M, N, K, alpha, A, lda, B, ldb, beta, Cm, ldc):
     getattr(lib(), f"ATL_{p}gemm")(TA, TB, M, N, K, a.arg, ptr(A), lda, ptr(B), ldb, b.arg, ptr(Cm), ldc)
 
 
+def clapack_geqrf(p, Order, M, N, A, lda, TAU):
+    """A = Q R (reference clapack_Xgeqrf, Clint/atlas-clp.base:538): R on/above the diagonal, reflectors below, TAU min(M,N)"""
+    f = getattr(lib(), f"clapack_{p}geqrf")
+    f.argtypes = [C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p]
+    return f(Order, M, N, ptr(A), lda, ptr(TAU))
+
+
 def clapack_getrf(p, Order, M, N, A, lda, ipiv):
     return getattr(lib(), f"clapack_{p}getrf")(Order, M, N, ptr(A), lda, ptr(ipiv))
 
@@ -217,6 +224,7 @@ for _p in "sdcz":
     globals()[f"cblas_{_p}trsm"] = _bind(f"cblas_{_p}trsm", cblas_trsm, _p)
     globals()[f"cblas_{_p}trmm"] = _bind(f"cblas_{_p}trmm", cblas_trmm, _p)
     globals()[f"clapack_{_p}getrf"] = _bind(f"clapack_{_p}getrf", clapack_getrf, _p)
+    globals()[f"clapack_{_p}geqrf"] = _bind(f"clapack_{_p}geqrf", clapack_geqrf, _p)
     globals()[f"clapack_{_p}potrf"] = _bind(f"clapack_{_p}potrf", clapack_potrf, _p)
     for _nm in ("gesv", "getrs", "getri", "posv", "potrs", "potri", "lauum", "trtri"):
         globals()[f"clapack_{_p}{_nm}"] = _bind(f"clapack_{_p}{_nm}", globals()[f"clapack_{_nm}"], _p)

@@ -14,7 +14,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(CSRC, "obj")
 LIB = os.path.join(HERE, "libatlas_b200.so")
-SOURCES = ["runtime.cu", "dgemm_tma.cu", "zgemm_tma.cu", "sgemm_ffma.cu", "sgemm_tc.cu", "cgemm_ffma.cu", "level3.cu", "lapack.cu", "lapack_inv.cu", "capi.cu", "probe.cu"]
+SOURCES = ["runtime.cu", "dgemm_tma.cu", "zgemm_tma.cu", "sgemm_ffma.cu", "sgemm_tc.cu", "cgemm_ffma.cu", "level3.cu", "lapack.cu", "lapack_inv.cu", "qr.cu", "capi.cu", "probe.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC",
               "--expt-relaxed-constexpr", "-diag-suppress", "177,550"]
 # (Round 1 compiled everything with -Xptxas -dlcm=cg on the hypothesis that stale L1 lines caused the LU look-ahead

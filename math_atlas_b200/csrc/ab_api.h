@@ -65,6 +65,14 @@ void getrf(int M, int N, T* A, size_t lda, int* d_ipiv, int* d_info);
 template <typename T>
 void potrf(int uplo, int N, T* A, size_t lda, int* d_info);
 
+// ---- QR (qr.cu): A = Q R, LAPACK storage (R above, reflector vectors below the diagonal), tau on the
+// device, min(M,N) entries (reference ATL_geqrf, Students/qr.base:594)
+template <typename T>
+void geqrf(int M, int N, T* A, size_t lda, T* d_tau);
+// Bt (cols x rows) <- transpose (conj = conjugate transpose) of B (rows x cols)
+template <typename T>
+void transpose_conj(int rows, int cols, const T* B, size_t ldb, T* Bt, size_t ldbt, bool conj);
+
 // ---- solve / inverse layer (lapack_inv.cu) ---------------------------------
 // B <- solution of op(A) X = B from getrf's factors; order/trans as ATL_getrs (atlas-lp.base:1631)
 template <typename T>

@@ -831,6 +831,56 @@ static int atl_potrf(int order, int uplo, int N, T* A, int lda) {
   return h_info;
 }
 
+// QR: clapack_Xgeqrf / ATL_Xgeqrf / Xgeqrf_ (reference Clint/atlas-clp.base:538-598, Students/qr.base:594-760).
+// RowMajor M x N is the column-major N x M matrix B in the same memory, for which the reference calls gelqf(N, M): B = L Q.
+// That is the QR factorisation of C = B^H (M x N): L = R^H, the reflector vectors come back conjugated in the rows of B and
+// tau is the same - so C is formed, factored and stored back conjugate-transposed; for complex types the reference's wrapper
+// then negates Im(TAU) (atlas-clp.base:590-596), as here.
+template <typename T>
+static int atl_geqrf(int order, int M, int N, T* A, int lda, T* TAU) {
+  const int MN = M < N ? M : N;
+  if (MN <= 0) return 0;
+  Operand<T> t(TAU, MN, 1, (size_t)MN, false, true);
+  if (order == ColMajor) {
+    Operand<T> a(A, M, N, (size_t)lda, true, true);
+    geqrf<T>(M, N, a.d, a.ld, t.d);
+    a.finish();
+  } else {
+    Operand<T> b(A, N, M, (size_t)lda, true, true);
+    init_pool_once();
+    T* Cm = nullptr;
+    const size_t ldc = ((size_t)M + 15) & ~(size_t)15;
+    AB_CUDA_CHECK(cudaMallocAsync(&Cm, sizeof(T) * ldc * (size_t)N, current_stream()));
+    transpose_conj<T>(N, M, b.d, b.ld, Cm, ldc, ST<T>::cplx);
+    geqrf<T>(M, N, Cm, ldc, t.d);
+    transpose_conj<T>(M, N, Cm, ldc, b.d, b.ld, ST<T>::cplx);
+    if (ST<T>::cplx) conj_inplace<T>(MN, 1, t.d, (size_t)MN);
+    AB_CUDA_CHECK(cudaFreeAsync(Cm, current_stream()));
+    b.finish();
+  }
+  t.finish();
+  sync_stream();
+  return 0;
+}
+template <typename T>
+static int cl_geqrf(const char* rout, int Order, int M, int N, T* A, int lda, T* TAU) {
+  int ierr = 0;
+  if (Order != RowMajor && Order != ColMajor) { ierr = -1; cblas_xerbla(1, rout, "Order must be %d or %d, but is set to %d\n", RowMajor, ColMajor, Order); }
+  if (M < 0) { ierr = -2; cblas_xerbla(2, rout, "M cannot be less than zero 0,; is set to %d.\n", M); }
+  if (N < 0) { ierr = -3; cblas_xerbla(3, rout, "N cannot be less than zero 0,; is set to %d.\n", N); }
+  if (Order == ColMajor) { if (lda < M || lda < 1) { ierr = -5; cblas_xerbla(5, rout, "lda must be >= MAX(M,1): lda=%d M=%d\n", lda, M); } }
+  else if (lda < N || lda < 1) { ierr = -5; cblas_xerbla(5, rout, "lda must be >= MAX(N,1): lda=%d N=%d\n", lda, N); }
+  if (!ierr) ierr = atl_geqrf<T>(Order, M, N, A, lda, TAU);
+  return ierr;
+}
+// ATL_Xgeqrf(M, N, A, lda, TAU, WORK, LWORK): LWORK < 0 is the workspace query (qr.base:700-760) - the device code needs no
+// caller workspace, the answer is the reference's N * nb with nb = 128; otherwise WORK is ignored.
+template <typename T>
+static int atl_geqrf_work(int M, int N, T* A, int lda, T* TAU, T* WORK, int LWORK) {
+  if (LWORK < 0) { if (WORK && !is_device_ptr(WORK)) WORK[0] = ST<T>::from_real((typename ST<T>::real)((N > 0 ? N : 1) * 128)); return 0; }
+  return atl_geqrf<T>(ColMajor, M, N, A, lda, TAU);
+}
+
 template <typename T>
 static void atl_laswp(int N, T* A, int lda, int K1, int K2, const int* piv, int inci) {
   if (N <= 0 || K2 <= K1) return;
@@ -1070,6 +1120,16 @@ static void f_getrf(const char* name, const int* m, const int* n, T* A, const in
   for (int i = 0; i < MN; i++) ipiv[i]++;
 }
 template <typename T>
+static void f_geqrf(const char* name, const int* m, const int* n, T* A, const int* lda, T* tau, T* work, const int* lwork, int* info) {
+  *info = 0;
+  if (*m < 0) *info = -1;
+  else if (*n < 0) *info = -2;
+  else if (*lda < imax(1, *m)) *info = -4;
+  else if (*lwork < imax(1, *n) && *lwork != -1) *info = -7;
+  if (*info) { int p = -*info; xerbla_(name, &p, strlen(name)); return; }
+  *info = atl_geqrf_work<T>(*m, *n, A, *lda, tau, work, *lwork == -1 ? -1 : *lwork);
+}
+template <typename T>
 static void f_potrf(const char* name, const char* ul, const int* n, T* A, const int* lda, int* info) {
   const int UL = f_uplo(ul);
   *info = 0;
@@ -1109,6 +1169,10 @@ extern "C" {
   int clapack_##P##getrf(int Order, int M, int N, T* A, int lda, int* ipiv) { return cl_getrf<T>("clapack_" #P "getrf", Order, M, N, A, lda, ipiv); } \
   int clapack_##P##potrf(int Order, int Uplo, int N, T* A, int lda) { return cl_potrf<T>("clapack_" #P "potrf", Order, Uplo, N, A, lda); } \
   int ATL_##P##getrf(int Order, int M, int N, T* A, int lda, int* ipiv) { return atl_getrf<T>(Order, M, N, A, lda, ipiv); }     \
+  int clapack_##P##geqrf(int Order, int M, int N, T* A, int lda, T* TAU) { return cl_geqrf<T>("clapack_" #P "geqrf", Order, M, N, A, lda, TAU); } \
+  int ATL_##P##geqrf(int M, int N, T* A, int lda, T* TAU, T* WORK, int LWORK) { return atl_geqrf_work<T>(M, N, A, lda, TAU, WORK, LWORK); } \
+  void P##geqrf_(const int* m, const int* n, T* A, const int* lda, T* tau, T* work, const int* lwork, int* info) {              \
+    f_geqrf<T>(UP "GEQRF", m, n, A, lda, tau, work, lwork, info); }                                                             \
   int ATL_##P##potrf(int Order, int Uplo, int N, T* A, int lda) { return atl_potrf<T>(Order, Uplo, N, A, lda); }                \
   void ATL_##P##laswp(int N, T* A, int lda, int K1, int K2, const int* piv, int inci) { atl_laswp<T>(N, A, lda, K1, K2, piv, inci); } \
   void P##gemm_(const char* ta, const char* tb, const int* m, const int* n, const int* k, const T* alpha, const T* A,           \
@@ -1158,6 +1222,12 @@ REAL_API(d, double, "D")
   int clapack_##P##getrf(int Order, int M, int N, void* A, int lda, int* ipiv) { return cl_getrf<T>("clapack_" #P "getrf", Order, M, N, MP(T, A), lda, ipiv); } \
   int clapack_##P##potrf(int Order, int Uplo, int N, void* A, int lda) { return cl_potrf<T>("clapack_" #P "potrf", Order, Uplo, N, MP(T, A), lda); } \
   int ATL_##P##getrf(int Order, int M, int N, R* A, int lda, int* ipiv) { return atl_getrf<T>(Order, M, N, MP(T, A), lda, ipiv); } \
+  int clapack_##P##geqrf(int Order, int M, int N, void* A, int lda, void* TAU) {                                                \
+    return cl_geqrf<T>("clapack_" #P "geqrf", Order, M, N, MP(T, A), lda, MP(T, TAU)); }                                        \
+  int ATL_##P##geqrf(int M, int N, R* A, int lda, R* TAU, R* WORK, int LWORK) {                                                 \
+    return atl_geqrf_work<T>(M, N, MP(T, A), lda, MP(T, TAU), MP(T, WORK), LWORK); }                                            \
+  void P##geqrf_(const int* m, const int* n, void* A, const int* lda, void* tau, void* work, const int* lwork, int* info) {     \
+    f_geqrf<T>(UP "GEQRF", m, n, MP(T, A), lda, MP(T, tau), MP(T, work), lwork, info); }                                        \
   int ATL_##P##potrf(int Order, int Uplo, int N, R* A, int lda) { return atl_potrf<T>(Order, Uplo, N, MP(T, A), lda); }         \
   void ATL_##P##laswp(int N, R* A, int lda, int K1, int K2, const int* piv, int inci) { atl_laswp<T>(N, MP(T, A), lda, K1, K2, piv, inci); } \
   void P##gemm_(const char* ta, const char* tb, const int* m, const int* n, const int* k, const void* alpha, const void* A,     \

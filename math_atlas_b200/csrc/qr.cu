@@ -1,0 +1,354 @@
+// QR factorisation: A = Q R by Householder reflectors, LAPACK storage - R on and above the
+// diagonal, the reflector vectors below it (unit diagonal implied), TAU the scalar factors, H(i) = I - tau_i v_i v_i^H,
+// Q = H(1) H(2) ... H(k).  Reference: ATL_geqrf / ATL_geqrr / ATL_geqr2 / ATL_larfg / ATL_larft / ATL_larfb
+// (Students/qr.base:594-2005, 1-141, 3033-3327, 3730-4859, 2085-2876) behind clapack_Xgeqrf (Clint/atlas-clp.base:538-598).
+//
+// The reference recurses on the column panel (ATL_geqrr) and applies block reflectors with GEMM/TRMM; the GPU version keeps
+// that structure with two fixed levels:
+//   * 32-column leaf (geqr2_panel_kernel): a grid of co-resident CTAs owns the rows of the panel; per column ONE pass
+//     accumulates |x|^2 and the inner products x^H A(:,c) with every remaining leaf column, one grid barrier reduces them in
+//     a fixed order, and a second pass forms v = x / (alpha - beta) and applies H^H to the leaf - a thread only ever
+//     re-reads the rows it wrote itself, so one barrier per column suffices (larfg + larf of geqr2 fused);
+//   * 128-column block: after each leaf its block reflector is applied to the rest of the block, then ONE block reflector
+//     for the whole block (T built from V^H V, larft) updates the trailing matrix with three GEMM-shaped calls (larfb):
+//     W = V^H C (DGEMM, K = rows), W = T^H W (TRMM), C -= V W (DGEMM, K = 128).
+// Differences to LAPACK's xLARFG that a caller could see: the norm is sqrt(sum |x|^2) without the scaled accumulation of
+// xNRM2 and without the re-scaling loop for |beta| < safmin (inputs with entries near the under/overflow thresholds).
+#include "ab_api.h"
+#include "dgemm_tma.h"
+#include <cfloat>
+#include <algorithm>
+
+namespace ab {
+
+namespace {
+constexpr int QR_W = 32;           // leaf width
+constexpr int QR_NB = 128;         // block width of the trailing update
+constexpr int QR_TH = 256;
+constexpr int QR_MAXG = 128;       // CTAs of the leaf grid (all must be co-resident)
+
+__device__ __forceinline__ void qr_grid_barrier(unsigned* counter, unsigned target) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    atomicAdd(counter, 1u);
+    volatile unsigned* vc = counter;
+    while (*vc < target) { }
+    __threadfence();
+  }
+  __syncthreads();
+}
+
+template <typename T> struct QrMath;
+template <> struct QrMath<float> {
+  static __device__ float norm2(float a) { return a * a; }
+  static __device__ float real(float a) { return a; }
+  static __device__ float imag(float) { return 0.f; }
+  static __device__ float rsqrt_(float s) { return sqrtf(s); }
+  static __device__ float recip(float a) { return 1.f / a; }
+};
+template <> struct QrMath<double> {
+  static __device__ double norm2(double a) { return a * a; }
+  static __device__ double real(double a) { return a; }
+  static __device__ double imag(double) { return 0.; }
+  static __device__ double rsqrt_(double s) { return sqrt(s); }
+  static __device__ double recip(double a) { return 1. / a; }
+};
+template <> struct QrMath<float2> {
+  static __device__ float norm2(float2 a) { return a.x * a.x + a.y * a.y; }
+  static __device__ float real(float2 a) { return a.x; }
+  static __device__ float imag(float2 a) { return a.y; }
+  static __device__ float rsqrt_(float s) { return sqrtf(s); }
+  static __device__ float2 recip(float2 a) {          // 1/a, Smith's formula (ATL_ladiv, qr.base:4860)
+    float t, d;
+    if (fabsf(a.x) >= fabsf(a.y)) { t = a.y / a.x; d = a.x + a.y * t; return make_float2(1.f / d, -t / d); }
+    t = a.x / a.y; d = a.x * t + a.y; return make_float2(t / d, -1.f / d);
+  }
+};
+template <> struct QrMath<double2> {
+  static __device__ double norm2(double2 a) { return a.x * a.x + a.y * a.y; }
+  static __device__ double real(double2 a) { return a.x; }
+  static __device__ double imag(double2 a) { return a.y; }
+  static __device__ double rsqrt_(double s) { return sqrt(s); }
+  static __device__ double2 recip(double2 a) {
+    double t, d;
+    if (fabs(a.x) >= fabs(a.y)) { t = a.y / a.x; d = a.x + a.y * t; return make_double2(1. / d, -t / d); }
+    t = a.x / a.y; d = a.x * t + a.y; return make_double2(t / d, -1. / d);
+  }
+};
+
+// Leaf: Householder QR of the Mp x w block at A (w <= 32), tau[0..min(Mp,w)).  ws: per column (1 + QR_W) partial sums per CTA
+// plus the diagonal row; counter: zeroed by the caller.
+//   part[j][cta][0]      = sum |x_r|^2 (real, stored in .x / the real itself)
+//   part[j][cta][1 + c]  = sum conj(x_r) A(r, c),  c > j
+//   drow[j][c]           = A(j, c) before the update (c >= j), written by the owner of row j
+template <typename T>
+__global__ void __launch_bounds__(QR_TH)
+geqr2_panel_kernel(int Mp, int w, T* A, size_t lda, T* tau, T* part, T* drow, unsigned* counter) {
+  using S = ST<T>;
+  using R = typename S::real;
+  using Q = QrMath<T>;
+  const int G = gridDim.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const int gtid = blockIdx.x * QR_TH + tid, gsz = G * QR_TH;
+  const int kmax = min(Mp, w);
+  __shared__ T s_red[QR_TH / 32][QR_W + 1];
+  __shared__ T s_tot[QR_W + 1];
+  __shared__ T s_scale, s_tauc;
+  for (int j = 0; j < kmax; j++) {
+    // ---- pass 1: partial sums over the rows this thread owns (r > j)
+    T acc[QR_W + 1];
+#pragma unroll
+    for (int c = 0; c <= QR_W; c++) acc[c] = S::zero();
+    for (int r = gtid; r < Mp; r += gsz) {
+      if (r < j) continue;
+      const T x = A[(size_t)r + (size_t)j * lda];
+      if (r == j) {                                     // the diagonal row: publish it
+#pragma unroll
+        for (int c = 0; c < QR_W; c++)
+          if (c >= j && c < w) drow[(size_t)j * QR_W + c] = A[(size_t)r + (size_t)c * lda];
+        continue;
+      }
+      acc[0] = S::add(acc[0], S::from_real(Q::norm2(x)));
+      const T xc = S::conj(x);
+#pragma unroll
+      for (int c = 0; c < QR_W; c++)
+        if (c > j && c < w) S::fma(acc[1 + c], xc, A[(size_t)r + (size_t)c * lda]);
+    }
+    // CTA reduction in a fixed order: lanes by shuffle, warps sequentially
+#pragma unroll
+    for (int c = 0; c <= QR_W; c++) {
+      T v = acc[c];
+#pragma unroll
+      for (int off = 16; off > 0; off >>= 1) {
+        T o;
+        if constexpr (S::cplx) { o.x = __shfl_xor_sync(0xffffffffu, v.x, off); o.y = __shfl_xor_sync(0xffffffffu, v.y, off); }
+        else o = __shfl_xor_sync(0xffffffffu, v, off);
+        v = S::add(v, o);
+      }
+      if (lane == 0) s_red[wid][c] = v;
+    }
+    __syncthreads();
+    if (tid <= QR_W) {
+      T v = S::zero();
+      for (int q = 0; q < QR_TH / 32; q++) v = S::add(v, s_red[q][tid]);
+      part[((size_t)j * G + blockIdx.x) * (QR_W + 1) + tid] = v;
+    }
+    qr_grid_barrier(counter, (unsigned)G * (unsigned)(j + 1));
+    // ---- every CTA adds the G partial results in the same order
+    if (tid <= QR_W) {
+      T v = S::zero();
+      for (int g = 0; g < G; g++) v = S::add(v, part[((size_t)j * G + g) * (QR_W + 1) + tid]);
+      s_tot[tid] = v;
+    }
+    __syncthreads();
+    if (tid == 0) {
+      // larfg (qr.base:3033 ff.): beta = -sign(re alpha) * ||(alpha, x)||, tau = (beta - alpha) / beta, v = x / (alpha - beta)
+      const T alpha = drow[(size_t)j * QR_W + j];
+      const R xn2 = Q::real(s_tot[0]);
+      T tauv = S::zero(), scale = S::zero();
+      R beta = Q::real(alpha);
+      if (!(xn2 == (R)0 && Q::imag(alpha) == (R)0)) {
+        const R nrm = Q::rsqrt_(Q::real(alpha) * Q::real(alpha) + Q::imag(alpha) * Q::imag(alpha) + xn2);
+        // sign rule as the reference's larfg: real alpha >= 0 -> negative beta (qr.base:3165); complex: Re(alpha) > 0 (:3243)
+        const bool neg = S::cplx ? (Q::real(alpha) > (R)0) : (Q::real(alpha) >= (R)0);
+        beta = neg ? -nrm : nrm;
+        if constexpr (S::cplx) { tauv.x = (beta - alpha.x) / beta; tauv.y = -alpha.y / beta; }
+        else tauv = (beta - alpha) / beta;
+        scale = Q::recip(S::sub(alpha, S::from_real(beta)));
+      }
+      s_scale = scale; s_tauc = S::conj(tauv);
+      if (blockIdx.x == 0) tau[j] = tauv;
+      s_tot[0] = S::from_real(beta);
+    }
+    __syncthreads();
+    const T scale = s_scale, tauc = s_tauc;
+    const bool identity = S::is_zero(tauc);
+    // ---- pass 2: v, and H^H applied to the leaf columns right of j
+    for (int r = gtid; r < Mp; r += gsz) {
+      if (r < j) continue;
+      T v;
+      if (r == j) { v = S::one(); A[(size_t)r + (size_t)j * lda] = s_tot[0]; }
+      else {
+        if (identity) continue;
+        v = S::mul(A[(size_t)r + (size_t)j * lda], scale);
+        A[(size_t)r + (size_t)j * lda] = v;
+      }
+      if (identity) continue;
+#pragma unroll
+      for (int c = 0; c < QR_W; c++) {
+        if (c > j && c < w) {
+          // w_c = A(j,c) + conj(scale) * sum conj(x) A(:,c);  A(r,c) -= conj(tau) * w_c * v_r
+          const T wc = S::add(drow[(size_t)j * QR_W + c], S::mul(S::conj(scale), s_tot[1 + c]));
+          T* p = A + (size_t)r + (size_t)c * lda;
+          *p = S::sub(*p, S::mul(S::mul(tauc, wc), v));
+        }
+      }
+    }
+    __syncthreads();      // s_tot / s_scale are rewritten in the next column
+  }
+}
+
+// V explicit: Vw (Mp x nb, leading dimension ldv) <- unit lower trapezoid of the factored block
+template <typename T>
+__global__ void qr_copy_v_kernel(int Mp, int nb, const T* A, size_t lda, T* V, size_t ldv) {
+  using S = ST<T>;
+  const int r = blockIdx.x * blockDim.x + threadIdx.x, c = blockIdx.y;
+  if (r >= Mp || c >= nb) return;
+  V[(size_t)r + (size_t)c * ldv] = r > c ? A[(size_t)r + (size_t)c * lda] : (r == c ? S::one() : S::zero());
+}
+
+// larft, forward / columnwise (qr.base:3730 ff.): T(i,i) = tau_i, T(0:i, i) = -tau_i * T(0:i,0:i) * G(0:i, i) with G = V^H V.
+// One CTA; column i needs the finished columns < i.  Below the diagonal T is zero.
+template <typename T>
+__global__ void __launch_bounds__(128) qr_larft_kernel(int nb, const T* tau, const T* G, int ldg, T* Tm, int ldt) {
+  using S = ST<T>;
+  extern __shared__ __align__(16) unsigned char qr_smem[];
+  T* Ts = reinterpret_cast<T*>(qr_smem);           // upper triangle, packed by columns: (a, b), a <= b, at b(b+1)/2 + a
+  const int a = threadIdx.x;
+  for (int i = 0; i < nb; i++) {
+    const T ti = tau[i];
+    if (a < i) {
+      T s = S::zero();
+      for (int b = a; b < i; b++) S::fma(s, Ts[b * (b + 1) / 2 + a], G[b + (size_t)i * ldg]);
+      Ts[i * (i + 1) / 2 + a] = S::mul(S::sub(S::zero(), ti), s);
+    } else if (a == i) Ts[i * (i + 1) / 2 + a] = ti;
+    __syncthreads();
+  }
+  for (int idx = a; idx < nb * nb; idx += blockDim.x) {
+    const int r = idx % nb, c = idx / nb;
+    Tm[r + (size_t)c * ldt] = r <= c ? Ts[c * (c + 1) / 2 + r] : S::zero();
+  }
+}
+
+struct QrScratch { unsigned* counter = nullptr; void* part = nullptr; void* drow = nullptr; size_t part_bytes = 0; int dev = -1; };
+thread_local QrScratch g_qr;
+
+int qr_grid_for(int Mp) {
+  static int cap[AB_MAX_DEV] = {};
+  int& c = cap[ab_dev()];
+  if (!c) {
+    int sms = 0;
+    AB_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ab_dev()));
+    c = std::min(QR_MAXG, std::max(1, sms - 16));     // one CTA per SM at most: co-resident on an otherwise idle device
+  }
+  return std::max(1, std::min(c, (Mp + QR_TH * 4 - 1) / (QR_TH * 4)));
+}
+
+template <typename T>
+void qr_leaf(int Mp, int w, T* A, size_t lda, T* tau) {
+  const int G = qr_grid_for(Mp);
+  QrScratch& q = g_qr;
+  const size_t need = sizeof(T) * (size_t)QR_W * G * (QR_W + 1);
+  if (q.dev != ab_dev() || q.part_bytes < sizeof(double2) * (size_t)QR_W * QR_MAXG * (QR_W + 1)) {
+    if (q.counter) { cudaFree(q.counter); cudaFree(q.part); cudaFree(q.drow); }
+    q.part_bytes = sizeof(double2) * (size_t)QR_W * QR_MAXG * (QR_W + 1);
+    AB_CUDA_CHECK(cudaMalloc(&q.counter, sizeof(unsigned)));
+    AB_CUDA_CHECK(cudaMalloc(&q.part, q.part_bytes));
+    AB_CUDA_CHECK(cudaMalloc(&q.drow, sizeof(double2) * QR_W * QR_W));
+    q.dev = ab_dev();
+  }
+  (void)need;
+  cudaStream_t st = current_stream();
+  AB_CUDA_CHECK(cudaMemsetAsync(q.counter, 0, sizeof(unsigned), st));
+  geqr2_panel_kernel<T><<<G, QR_TH, 0, st>>>(Mp, w, A, lda, tau, static_cast<T*>(q.part), static_cast<T*>(q.drow), q.counter);
+  count_launch();
+  AB_CUDA_CHECK(cudaGetLastError());
+}
+
+// C (Mp x n) <- (I - V T^H V^H) C with V = Vw (Mp x nb, explicit), T nb x nb upper; W: nb x n scratch
+template <typename T>
+void qr_larfb(int Mp, int n, int nb, const T* Vw, size_t ldv, const T* Tm, int ldt, T* C, size_t ldc, T* W) {
+  using S = ST<T>;
+  if (n <= 0 || Mp <= 0) return;
+  const int ct = S::cplx ? ConjTrans : TransT;
+  gemm<T>(ct, NoTrans, nb, n, Mp, S::one(), Vw, ldv, C, ldc, S::zero(), W, (size_t)nb);
+  trmm<T>(Left, Upper, ct, NonUnit, nb, n, S::one(), Tm, (size_t)ldt, W, (size_t)nb);
+  gemm<T>(NoTrans, NoTrans, Mp, n, nb, S::from_real(-1), Vw, ldv, W, (size_t)nb, S::one(), C, ldc);
+}
+
+// explicit V and T of the nb factored columns at A (Mp rows)
+template <typename T>
+void qr_build_vt(int Mp, int nb, const T* A, size_t lda, const T* tau, T* Vw, size_t ldv, T* G, T* Tm) {
+  using S = ST<T>;
+  cudaStream_t st = current_stream();
+  qr_copy_v_kernel<T><<<dim3((Mp + 255) / 256, nb), 256, 0, st>>>(Mp, nb, A, lda, Vw, ldv);
+  count_launch();
+  const int ct = S::cplx ? ConjTrans : TransT;
+  gemm<T>(ct, NoTrans, nb, nb, Mp, S::one(), Vw, ldv, Vw, ldv, S::zero(), G, (size_t)nb);
+  qr_larft_kernel<T><<<1, 128, sizeof(T) * nb * (nb + 1) / 2, st>>>(nb, tau, G, nb, Tm, nb);
+  count_launch();
+  AB_CUDA_CHECK(cudaGetLastError());
+}
+}  // namespace
+
+// A (M x N, device) <- its QR factorisation, tau (device, min(M,N) entries)
+template <typename T>
+void geqrf(int M, int N, T* A, size_t lda, T* tau) {
+  const int MN = std::min(M, N);
+  if (MN <= 0) return;
+  static PerDeviceOnce attr_once;
+  attr_once([] { AB_CUDA_CHECK(cudaFuncSetAttribute(qr_larft_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(T) * QR_NB * (QR_NB + 1) / 2))); });
+  const size_t ldv = ((size_t)M + 15) & ~(size_t)15;
+  // scratch: V (ldv x NB), W (NB x N), G and T (NB x NB each)
+  T* Vw = static_cast<T*>(workspace(sizeof(T) * (ldv * QR_NB + (size_t)QR_NB * N + 2 * QR_NB * QR_NB), 6));
+  T* W = Vw + ldv * QR_NB;
+  T* G = W + (size_t)QR_NB * N;
+  T* Tm = G + QR_NB * QR_NB;
+  set_gemm_splitk_allowed(true);       // V^H V and V^H C are short-and-wide products with K = rows: split-K territory
+  for (int j0 = 0; j0 < MN; j0 += QR_NB) {
+    const int nb = std::min(QR_NB, MN - j0);
+    const int Mp = M - j0;
+    T* Ab = A + (size_t)j0 + (size_t)j0 * lda;
+    // leaves inside the block, each followed by its block reflector on the rest of the block
+    for (int l0 = 0; l0 < nb; l0 += QR_W) {
+      const int lw = std::min(QR_W, nb - l0);
+      T* Al = Ab + (size_t)l0 + (size_t)l0 * lda;
+      qr_leaf<T>(Mp - l0, lw, Al, lda, tau + j0 + l0);
+      const int rest = nb - l0 - lw;
+      if (rest > 0) {
+        qr_build_vt<T>(Mp - l0, lw, Al, lda, tau + j0 + l0, Vw, ldv, G, Tm);
+        qr_larfb<T>(Mp - l0, rest, lw, Vw, ldv, Tm, lw, Al + (size_t)lw * lda, lda, W);
+      }
+    }
+    const int ntrail = N - j0 - nb;
+    if (ntrail > 0) {
+      qr_build_vt<T>(Mp, nb, Ab, lda, tau + j0, Vw, ldv, G, Tm);
+      qr_larfb<T>(Mp, ntrail, nb, Vw, ldv, Tm, nb, Ab + (size_t)nb * lda, lda, W);
+    }
+  }
+  set_gemm_splitk_allowed(false);
+}
+
+// B (N x M... ) helper for the row-major entry: Bt (cols x rows, ldbt) <- conj-transpose (or transpose) of B (rows x cols, ldb)
+template <typename T>
+__global__ void qr_transpose_kernel(int rows, int cols, const T* B, size_t ldb, T* Bt, size_t ldbt, int conj) {
+  using S = ST<T>;
+  __shared__ T tile[32][33];
+  const int r0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int r = r0 + threadIdx.x, c = c0 + i;
+    if (r < rows && c < cols) tile[i][threadIdx.x] = B[(size_t)r + (size_t)c * ldb];
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int c = c0 + threadIdx.x, r = r0 + i;
+    if (r < rows && c < cols) { T v = tile[threadIdx.x][i]; Bt[(size_t)c + (size_t)r * ldbt] = conj ? S::conj(v) : v; }
+  }
+}
+template <typename T>
+void transpose_conj(int rows, int cols, const T* B, size_t ldb, T* Bt, size_t ldbt, bool conj) {
+  if (rows <= 0 || cols <= 0) return;
+  qr_transpose_kernel<T><<<dim3((rows + 31) / 32, (cols + 31) / 32), dim3(32, 8), 0, current_stream()>>>(rows, cols, B, ldb, Bt, ldbt, conj ? 1 : 0);
+  count_launch();
+  AB_CUDA_CHECK(cudaGetLastError());
+}
+
+#define AB_QR_INST(T)                                               \
+  template void geqrf<T>(int, int, T*, size_t, T*);                 \
+  template void transpose_conj<T>(int, int, const T*, size_t, T*, size_t, bool);
+AB_QR_INST(float)
+AB_QR_INST(double)
+AB_QR_INST(float2)
+AB_QR_INST(double2)
+
+}  // namespace ab

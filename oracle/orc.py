@@ -165,6 +165,12 @@ class Oracle(_Base):
     def potrf(self, pre, uplo, N, a, leaf=4):
         return getattr(self.lib, f"orc_{pre}potrf_rec")(uplo, N, _p(a), self._ld(a), leaf if not CPLX[pre] else 1)
 
+    def geqr2(self, pre, M, N, a):
+        """unblocked Householder QR in place (reference ATL_geqr2, Students/qr.base:78); returns tau (min(M,N))"""
+        tau = np.zeros(max(min(M, N), 1), dtype=DT[pre])
+        getattr(self.lib, f"orc_{pre}geqr2")(M, N, _p(a), self._ld(a), _p(tau))
+        return tau[:min(M, N)]
+
     # ---- solve / inverse layer (SURVEY 8(f) item 2); a, b are modified in place
     def getrs(self, pre, order, trans, N, NRHS, a, ipiv, b):
         ipiv = np.ascontiguousarray(ipiv, dtype=np.int32)
@@ -327,6 +333,31 @@ class Ref(_Base):
 # ------------------------------------------------------------------------------------------
 # The reference testers' pass/fail formulas (numpy; the norms are the oracle's C restatements)
 # ------------------------------------------------------------------------------------------
+def qr_apply_q(pre, M, N, QR, tau, X, adjoint=False):
+    """Q X (or Q^H X) from geqrf's output by applying the reflectors one by one (numpy, wide precision); X has M rows."""
+    wide = np.complex128 if CPLX[pre] else np.float64
+    Y = X.astype(wide).copy()
+    k = min(M, N)
+    order = range(k) if adjoint else range(k - 1, -1, -1)
+    for i in order:
+        v = np.zeros(M, dtype=wide); v[i] = 1; v[i + 1:] = QR[i + 1:M, i]
+        t = np.conj(tau[i]) if adjoint else tau[i]
+        Y -= np.outer(t * v, np.conj(v) @ Y)
+    return Y
+
+
+def qr_resid(pre, M, N, A0, QR, tau):
+    """qrtst (Students/qr.base:5383 ff.): ||A - Q R||_1 / (||A||_1 eps max(M,N)) and ||I - Q^H Q||_1 / (eps M)."""
+    wide = np.complex128 if CPLX[pre] else np.float64
+    k = min(M, N)
+    Rm = np.zeros((M, N), dtype=wide); Rm[:k, :] = np.triu(QR[:k, :N].astype(wide))
+    QRm = qr_apply_q(pre, M, N, QR, tau, Rm)
+    r1 = _nrm1(A0[:M, :N].astype(wide) - QRm) / (_nrm1(A0[:M, :N]) * eps_of(pre) * max(M, N))
+    Q = qr_apply_q(pre, M, N, QR, tau, np.eye(M, dtype=wide))
+    r2 = _nrm1(np.eye(M) - np.conj(Q.T) @ Q) / (eps_of(pre) * M)
+    return r1, r2
+
+
 def eps_of(pre):
     return float(np.finfo(RDT[pre]).eps)  # == ATL_Xepsilon(): 2^-23 / 2^-52
 

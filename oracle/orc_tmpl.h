@@ -778,6 +778,97 @@ int FN(getri)(int N, S* A, int lda, const int* ipiv, int nb) {
   return 0;
 }
 
+/* ---- QR: unblocked Householder factorisation, the semantics every blocked / recursive variant of the reference reduces to
+ * (ATL_geqr2, Students/qr.base:78-141; ATL_larfg :3140-3327; ATL_larf :2877-3032).  A = Q R, R on/above the diagonal,
+ * v(i+1:m) of H(i) = I - tau v v^H below it, Q = H(1)...H(k).  geqr2 applies H(i)^H (conj(tau)) to the columns right of i. */
+static R FN(nrm2)(int n, const S* x) {        /* scaled sum of squares (reference BLAS ATL_Xrefnrm2, Antoine/atlrefblas.base) */
+  R scale = 0, ssq = 1;
+  for (int i = 0; i < n; i++) {
+#ifdef ORC_CPLX
+    const R parts[2] = {x[i].re, x[i].im};
+    for (int q = 0; q < 2; q++) {
+      R a = parts[q] < 0 ? -parts[q] : parts[q];
+#else
+    {
+      R a = x[i] < 0 ? -x[i] : x[i];
+#endif
+      if (a != 0) {
+        if (scale < a) { ssq = 1 + ssq * (scale / a) * (scale / a); scale = a; }
+        else ssq += (a / scale) * (a / scale);
+      }
+    }
+  }
+  return scale * (R)sqrt((double)ssq);
+}
+static void FN(larfg)(int n, S* alpha, S* x, S* tau) {
+  const R safmin_eps = (R)ORC_SAFMIN / ((R)(sizeof(R) == 4 ? 5.9604644775390625e-8 : 1.1102230246251565e-16));
+  if (n < 1) { *tau = S_ZERO; return; }
+  R xnorm = FN(nrm2)(n - 1, x);
+#ifndef ORC_CPLX
+  if (xnorm == 0) { *tau = 0; return; }
+  R betap = (R)hypot((double)*alpha, (double)xnorm);
+  R beta = (*alpha >= 0) ? -betap : betap;
+  if (betap < safmin_eps) {
+    const R rs = 1 / safmin_eps;
+    int knt = 0;
+    do { knt++; for (int i = 0; i < n - 1; i++) x[i] *= rs; beta *= rs; *alpha *= rs; betap = beta >= 0 ? beta : -beta; } while (betap < safmin_eps && knt < 20);
+    xnorm = FN(nrm2)(n - 1, x);
+    beta = (R)hypot((double)*alpha, (double)xnorm);
+    if (*alpha > 0) beta = -beta;
+    *tau = (beta - *alpha) / beta;
+    const R sc = 1 / (*alpha - beta);
+    for (int i = 0; i < n - 1; i++) x[i] *= sc;
+    *alpha = beta;
+    for (int j = 0; j < knt; j++) *alpha *= (R)ORC_SAFMIN;
+  } else {
+    *tau = (beta - *alpha) / beta;
+    const R sc = 1 / (*alpha - beta);
+    for (int i = 0; i < n - 1; i++) x[i] *= sc;
+    *alpha = beta;
+  }
+#else
+  R ar = alpha->re, ai = alpha->im;
+  if (xnorm == 0 && ai == 0) { *tau = S_ZERO; return; }
+  R betap = (R)sqrt((double)ar * ar + (double)ai * ai + (double)xnorm * xnorm);     /* lapy3 */
+  R beta = betap;
+  if (ar > 0) beta = -betap;
+  int knt = 0;
+  if (betap < (R)ORC_SAFMIN) {
+    const R rs = 1 / (R)ORC_SAFMIN;
+    while (betap < (R)ORC_SAFMIN) { knt++; for (int i = 0; i < n - 1; i++) { x[i].re *= rs; x[i].im *= rs; } beta *= rs; betap *= rs; ai *= rs; ar *= rs; }
+    xnorm = FN(nrm2)(n - 1, x);
+    beta = (R)sqrt((double)ar * ar + (double)ai * ai + (double)xnorm * xnorm);
+    if (ar > 0) beta = -beta;
+  }
+  *tau = MK((beta - ar) / beta, -ai / beta);
+  const S sc = S_INV(MK(ar - beta, ai));
+  for (int i = 0; i < n - 1; i++) x[i] = S_MUL(x[i], sc);
+  R a = beta;
+  for (int j = 0; j < knt; j++) a *= (R)ORC_SAFMIN;
+  *alpha = MK(a, 0);
+#endif
+}
+int FN(geqr2)(int M, int N, S* A, int lda, S* tau) {
+  const int k = M < N ? M : N;
+  for (int i = 0; i < k; i++) {
+    const int t = (i + 1 < M - 1) ? i + 1 : M - 1;
+    FN(larfg)(M - i, &EL(A, lda, i, i), &EL(A, lda, t, i), &tau[i]);
+    if (i < N - 1 && !S_ISZERO(tau[i])) {
+      const S aii = EL(A, lda, i, i);
+      const S tc = S_CONJ(tau[i]);
+      EL(A, lda, i, i) = S_ONE;
+      for (int c = i + 1; c < N; c++) {           /* larf, Left: w = C^H v ; C -= tau v w^H */
+        S w = S_ZERO;
+        for (int r = i; r < M; r++) w = S_ADD(w, S_MUL(S_CONJ(EL(A, lda, r, i)), EL(A, lda, r, c)));
+        const S tw = S_MUL(tc, w);
+        for (int r = i; r < M; r++) EL(A, lda, r, c) = S_SUB(EL(A, lda, r, c), S_MUL(EL(A, lda, r, i), tw));
+      }
+      EL(A, lda, i, i) = aii;
+    }
+  }
+  return 0;
+}
+
 #undef S
 #undef MK
 #undef S_ZERO
