@@ -12,8 +12,8 @@
 #    this repo.  What IS built is the code the reference itself trusts in its
 #    testers: the reference BLAS ATL_Xref* (Antoine/atlrefblas.base), the tester generators /
 #    norms (Clint/atlas-tst.base) and the real recursive LAPACK drivers ATL_getrfC / ATL_getf2 /
-#    ATL_laswp / ATL_potrf{L,U} and the solve/inverse layer ATL_getrs / potrs / trtri / lauum /
-#    getri (Clint/atlas-lp.base) linked against that reference BLAS through
+#    ATL_laswp / ATL_potrf{L,U}, the solve/inverse layer ATL_getrs / potrs / trtri / lauum /
+#    getri (Clint/atlas-lp.base) and the unblocked QR ATL_geqr2 / larfg / larf (Students/qr.base) linked against that reference BLAS through
 #    oracle/ref_shim/cblas_to_ref.c (our glue: cblas_* -> ATL_Xref*).
 #  * oracle/ref_shim/*.h are ours: the few configure-probed facts (type sizes, IEEE limits,
 #    L1 size) the sources need.
@@ -53,6 +53,11 @@ for t in s:SREAL d:DREAL c:SCPLX z:DCPLX; do
     gcc $CF -D$D -c $A/src/lapack/ATL_$f.c -o obj/${p}_${f}_C.o
     gcc $CF -D$D -DRowMajor_ -c $A/src/lapack/ATL_$f.c -o obj/${p}_${f}_R.o
   done
+  # unblocked QR (Students/qr.base: ATL_geqr2 / ATL_larfg / ATL_larf and the scalar helpers they call)
+  for f in lapack/ATL_geqr2 lapack/ATL_larfg lapack/ATL_larf lapack/ATL_lapy3 lapack/ATL_ladiv; do
+    gcc $CF -D$D -c $A/src/$f.c -o obj/${p}_$(basename $f).o
+  done
+  if [ $p = s ] || [ $p = d ]; then gcc $CF -D$D -c $A/src/lapack/ATL_lapy2.c -o obj/${p}_lapy2.o; fi
   if [ $p = c ] || [ $p = z ]; then
     for f in testing/ATL_henrm lapack/ATL_potrfRL lapack/ATL_potrfRU auxil/ATL_cplxinvert auxil/ATL_cplxdivide; do
       gcc $CF -D$D -c $A/src/$f.c -o obj/${p}_$(basename $f).o

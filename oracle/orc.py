@@ -243,6 +243,13 @@ class Ref(_Base):
         getattr(self.lib, f"ATL_{pre}gegen")(M, N, _p(a), lda, C.c_int(seed))
         return a
 
+    def geqr2(self, pre, M, N, a):
+        """the reference's own unblocked QR (ATL_Xgeqr2, Students/qr.base:78) on its reference BLAS"""
+        tau = np.zeros(max(min(M, N), 1), dtype=DT[pre])
+        work = np.zeros(max(N, 1), dtype=DT[pre])
+        getattr(self.lib, f"ATL_{pre}geqr2")(M, N, _p(a), self._ld(a), _p(tau), _p(work))
+        return tau[:min(M, N)]
+
     def genrm1(self, pre, M, N, a): return float(getattr(self.lib, f"ATL_{pre}genrm1")(M, N, _p(a), self._ld(a)))
     def gediffnrm1(self, pre, M, N, a, b):
         return float(getattr(self.lib, f"ATL_{pre}gediffnrm1")(M, N, _p(a), self._ld(a), _p(b), self._ld(b)))

@@ -84,3 +84,22 @@ void Mjoin(PATL, set)(long N, const SCALAR alpha, TYPE* X, long incX) {
   for (i = 0; i < N; i++) X[i * incX] = alpha;
 #endif
 }
+
+/* ---- what the reference's unblocked QR (ATL_geqr2 / ATL_larfg / ATL_larf, Students/qr.base) calls: nrm2, gemv, ger / gerc */
+#ifdef TCPLX
+TYPE Mjoin(Mjoin(cblas_, UPR), Mjoin(PRE, nrm2))(const int N, const TYPE* X, const int incX) {
+  return Mjoin(Mjoin(Mjoin(ATL_, UPR), PRE), refnrm2)(N, X, incX);
+}
+void CB(gerc)(const enum ATLAS_ORDER O, const int M, const int N, const SCALAR alpha, const TYPE* X, const int incX, const TYPE* Y,
+              const int incY, TYPE* A, const int lda) { REF(gerc)(M, N, alpha, X, incX, Y, incY, A, lda); }
+#else
+TYPE CB(nrm2)(const int N, const TYPE* X, const int incX) { return REF(nrm2)(N, X, incX); }
+void CB(ger)(const enum ATLAS_ORDER O, const int M, const int N, const SCALAR alpha, const TYPE* X, const int incX, const TYPE* Y,
+             const int incY, TYPE* A, const int lda) { REF(ger)(M, N, alpha, X, incX, Y, incY, A, lda); }
+#endif
+void CB(gemv)(const enum ATLAS_ORDER O, const enum ATLAS_TRANS TA, const int M, const int N, const SCALAR alpha, const TYPE* A,
+              const int lda, const TYPE* X, const int incX, const SCALAR beta, TYPE* Y, const int incY) {
+  /* the reference BLAS takes (length of y, length of x), cblas the shape of A (Antoine/atlrefblas.base:2593-2760) */
+  if (TA == AtlasNoTrans) REF(gemv)(TA, M, N, alpha, A, lda, X, incX, beta, Y, incY);
+  else REF(gemv)(TA, N, M, alpha, A, lda, X, incX, beta, Y, incY);
+}

@@ -48,5 +48,9 @@ for pre in "sdcz":
         A0 = orc.lltgen(ref, pre, uplo, 37, 39, 37 * 1029 + 39)
         a = A0.copy(order="F"); info = ref.potrf(pre, uplo, 37, a)
         out[f"{pre}_potrf_{nm}_in"] = A0; out[f"{pre}_potrf_{nm}_out"] = a; out[f"{pre}_potrf_{nm}_info"] = np.array([info])
+    for M_, N_ in ((45, 30), (30, 45)):                      # unblocked QR of the reference (ATL_Xgeqr2, Students/qr.base:78)
+        A0 = ref.gegen(pre, M_, N_, M_ + 2, M_ * N_ + 77)
+        a = A0.copy(order="F"); tau = ref.geqr2(pre, M_, N_, a)
+        out[f"{pre}_geqr2_{M_}x{N_}_qr"] = a; out[f"{pre}_geqr2_{M_}x{N_}_tau"] = tau.copy()
 np.savez_compressed(os.path.join(os.path.dirname(os.path.abspath(__file__)), "ref_vectors.npz"), **out)
 print("wrote", len(out), "arrays")

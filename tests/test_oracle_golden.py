@@ -57,3 +57,13 @@ def test_lapack_golden(oracle, pre):
         assert info == int(G[f"{pre}_potrf_{nm}_info"][0]) == 0
         tri = np.triu_indices(37) if uplo == Upper else np.tril_indices(37)
         assert np.max(np.abs(a[:37][tri] - G[f"{pre}_potrf_{nm}_out"][:37][tri])) <= 64 * eps_of(pre) * 37 * np.max(np.abs(a[:37][tri]))
+
+
+@pytest.mark.parametrize("pre", "sdcz")
+def test_qr_golden(oracle, pre):
+    """oracle geqr2 against the committed output of the reference's ATL_Xgeqr2 (tests/golden/make_golden.py)"""
+    for M_, N_ in ((45, 30), (30, 45)):
+        A0 = oracle.gegen(pre, M_, N_, M_ + 2, M_ * N_ + 77)
+        a = A0.copy(order="F"); tau = oracle.geqr2(pre, M_, N_, a)
+        assert np.max(np.abs(a - G[f"{pre}_geqr2_{M_}x{N_}_qr"])) <= 256 * eps_of(pre) * max(M_, N_)
+        assert np.max(np.abs(tau - G[f"{pre}_geqr2_{M_}x{N_}_tau"])) <= 256 * eps_of(pre)

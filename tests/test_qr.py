@@ -32,6 +32,18 @@ def test_oracle_geqr2_matches_lapack_and_tester(oracle, pre, M, N):
     assert r1 < 10.0 and r2 < 10.0, (r1, r2)
 
 
+@pytest.mark.parametrize("pre", cases.TYPES)
+@pytest.mark.parametrize("M,N", [(9, 6), (64, 64), (40, 90), (200, 33)])
+def test_oracle_geqr2_pinned_to_reference(oracle, ref, pre, M, N):
+    """the restatement against the reference's own ATL_Xgeqr2 / ATL_Xlarfg / ATL_Xlarf (oracle/_ref, built from Students/qr.base)"""
+    A0 = _gen(oracle, pre, M, N, M + 1, M * N + 9)
+    a, b = A0.copy(order="F"), A0.copy(order="F")
+    tau_o = oracle.geqr2(pre, M, N, a)
+    tau_r = ref.geqr2(pre, M, N, b)
+    assert np.abs(a - b).max() < TOL[pre] * max(M, N)
+    assert np.abs(tau_o - tau_r).max() < TOL[pre] * 10
+
+
 def _gpu_geqrf(ab, pre, order, M, N, A, lda, tau):
     return getattr(ab, f"clapack_{pre}geqrf")(order, M, N, A, lda, tau)
 
