@@ -77,11 +77,27 @@ template <> struct QrMath<double2> {
   }
 };
 
-// Leaf: Householder QR of the Mp x w block at A (w <= 32), tau[0..min(Mp,w)).  ws: per column (1 + QR_W) partial sums per CTA
-// plus the diagonal row; counter: zeroed by the caller.
-//   part[j][cta][0]      = sum |x_r|^2 (real, stored in .x / the real itself)
+// Leaf: Householder QR of the Mp x w block at A (w <= 32), tau[0..min(Mp,w)).
+// Thread layout: a CTA owns QR_ROWS = 64 rows per sweep; warp q of 8 serves row half q / 4 (32 consecutive rows, one per lane:
+// every global access is a coalesced 256-byte run) and column group q % 4 (8 of the 32 leaf columns).  Sweeps advance by
+// gridDim.x * 64 rows.  Per column j:
+//   pass 1  x = A(r, j); acc[c] += conj(x) A(r, c) for the warp's columns c > j, |x|^2 by column group 0; lanes are reduced
+//           by shuffle, the two row halves through shared memory, the CTA's 33 partial sums go to part[j][cta][.];
+//   barrier every CTA then adds the G partial results in the same order;
+//   larfg   beta, tau, scale = 1 / (alpha - beta) (thread 0 of every CTA, identical arithmetic);
+//   pass 2  v = x * scale, A(r, c) -= conj(tau) * w_c * v for the warp's columns; after a CTA barrier column group 0 stores v.
+// A thread re-reads only rows it wrote itself, so one grid barrier per column is enough.
+//   part[j][cta][0]      = sum |x_r|^2
 //   part[j][cta][1 + c]  = sum conj(x_r) A(r, c),  c > j
-//   drow[j][c]           = A(j, c) before the update (c >= j), written by the owner of row j
+//   drow[j][c]           = A(j, c) before the update (c >= j), written by the owners of row j
+constexpr int QR_CG = 4, QR_CPG = QR_W / QR_CG, QR_ROWS = 64;
+
+template <typename T>
+__device__ __forceinline__ T qr_shfl_xor(T v, int off) {
+  if constexpr (ST<T>::cplx) { T o; o.x = __shfl_xor_sync(0xffffffffu, v.x, off); o.y = __shfl_xor_sync(0xffffffffu, v.y, off); return o; }
+  else return __shfl_xor_sync(0xffffffffu, v, off);
+}
+
 template <typename T>
 __global__ void __launch_bounds__(QR_TH)
 geqr2_panel_kernel(int Mp, int w, T* A, size_t lda, T* tau, T* part, T* drow, unsigned* counter) {
@@ -89,50 +105,46 @@ geqr2_panel_kernel(int Mp, int w, T* A, size_t lda, T* tau, T* part, T* drow, un
   using R = typename S::real;
   using Q = QrMath<T>;
   const int G = gridDim.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-  const int gtid = blockIdx.x * QR_TH + tid, gsz = G * QR_TH;
+  const int cg = wid % QR_CG, half = wid / QR_CG;
+  const int c0 = cg * QR_CPG;                         // this warp's columns c0 .. c0 + 7
+  const int r_first = blockIdx.x * QR_ROWS + half * 32 + lane, r_step = G * QR_ROWS;
   const int kmax = min(Mp, w);
-  __shared__ T s_red[QR_TH / 32][QR_W + 1];
+  __shared__ T s_red[2][QR_W + 1];
   __shared__ T s_tot[QR_W + 1];
-  __shared__ T s_scale, s_tauc;
+  __shared__ T s_scale, s_tauc, s_beta;
   for (int j = 0; j < kmax; j++) {
-    // ---- pass 1: partial sums over the rows this thread owns (r > j)
-    T acc[QR_W + 1];
+    // ---- pass 1
+    T acc[QR_CPG], nrm = S::zero();
 #pragma unroll
-    for (int c = 0; c <= QR_W; c++) acc[c] = S::zero();
-    for (int r = gtid; r < Mp; r += gsz) {
+    for (int q = 0; q < QR_CPG; q++) acc[q] = S::zero();
+    for (int r = r_first; r < Mp; r += r_step) {
       if (r < j) continue;
-      const T x = A[(size_t)r + (size_t)j * lda];
-      if (r == j) {                                     // the diagonal row: publish it
+      if (r == j) {                                     // the diagonal row: publish this warp's part of it
 #pragma unroll
-        for (int c = 0; c < QR_W; c++)
-          if (c >= j && c < w) drow[(size_t)j * QR_W + c] = A[(size_t)r + (size_t)c * lda];
+        for (int q = 0; q < QR_CPG; q++)
+          if (c0 + q >= j && c0 + q < w) drow[(size_t)j * QR_W + c0 + q] = A[(size_t)r + (size_t)(c0 + q) * lda];
         continue;
       }
-      acc[0] = S::add(acc[0], S::from_real(Q::norm2(x)));
+      const T x = A[(size_t)r + (size_t)j * lda];
+      if (cg == 0) nrm = S::add(nrm, S::from_real(Q::norm2(x)));
       const T xc = S::conj(x);
 #pragma unroll
-      for (int c = 0; c < QR_W; c++)
-        if (c > j && c < w) S::fma(acc[1 + c], xc, A[(size_t)r + (size_t)c * lda]);
+      for (int q = 0; q < QR_CPG; q++)
+        if (c0 + q > j && c0 + q < w) S::fma(acc[q], xc, A[(size_t)r + (size_t)(c0 + q) * lda]);
     }
-    // CTA reduction in a fixed order: lanes by shuffle, warps sequentially
 #pragma unroll
-    for (int c = 0; c <= QR_W; c++) {
-      T v = acc[c];
+    for (int q = 0; q < QR_CPG; q++) {
 #pragma unroll
-      for (int off = 16; off > 0; off >>= 1) {
-        T o;
-        if constexpr (S::cplx) { o.x = __shfl_xor_sync(0xffffffffu, v.x, off); o.y = __shfl_xor_sync(0xffffffffu, v.y, off); }
-        else o = __shfl_xor_sync(0xffffffffu, v, off);
-        v = S::add(v, o);
-      }
-      if (lane == 0) s_red[wid][c] = v;
+      for (int off = 16; off > 0; off >>= 1) acc[q] = S::add(acc[q], qr_shfl_xor<T>(acc[q], off));
+      if (lane == 0) s_red[half][1 + c0 + q] = acc[q];
+    }
+    if (cg == 0) {
+#pragma unroll
+      for (int off = 16; off > 0; off >>= 1) nrm = S::add(nrm, qr_shfl_xor<T>(nrm, off));
+      if (lane == 0) s_red[half][0] = nrm;
     }
     __syncthreads();
-    if (tid <= QR_W) {
-      T v = S::zero();
-      for (int q = 0; q < QR_TH / 32; q++) v = S::add(v, s_red[q][tid]);
-      part[((size_t)j * G + blockIdx.x) * (QR_W + 1) + tid] = v;
-    }
+    if (tid <= QR_W) part[((size_t)j * G + blockIdx.x) * (QR_W + 1) + tid] = S::add(s_red[0][tid], s_red[1][tid]);
     qr_grid_barrier(counter, (unsigned)G * (unsigned)(j + 1));
     // ---- every CTA adds the G partial results in the same order
     if (tid <= QR_W) {
@@ -142,49 +154,57 @@ geqr2_panel_kernel(int Mp, int w, T* A, size_t lda, T* tau, T* part, T* drow, un
     }
     __syncthreads();
     if (tid == 0) {
-      // larfg (qr.base:3033 ff.): beta = -sign(re alpha) * ||(alpha, x)||, tau = (beta - alpha) / beta, v = x / (alpha - beta)
+      // larfg (qr.base:3140 ff.): beta = -sign(re alpha) * ||(alpha, x)||, tau = (beta - alpha) / beta, v = x / (alpha - beta)
       const T alpha = drow[(size_t)j * QR_W + j];
       const R xn2 = Q::real(s_tot[0]);
       T tauv = S::zero(), scale = S::zero();
       R beta = Q::real(alpha);
       if (!(xn2 == (R)0 && Q::imag(alpha) == (R)0)) {
-        const R nrm = Q::rsqrt_(Q::real(alpha) * Q::real(alpha) + Q::imag(alpha) * Q::imag(alpha) + xn2);
+        const R nrm2 = Q::rsqrt_(Q::real(alpha) * Q::real(alpha) + Q::imag(alpha) * Q::imag(alpha) + xn2);
         // sign rule as the reference's larfg: real alpha >= 0 -> negative beta (qr.base:3165); complex: Re(alpha) > 0 (:3243)
         const bool neg = S::cplx ? (Q::real(alpha) > (R)0) : (Q::real(alpha) >= (R)0);
-        beta = neg ? -nrm : nrm;
+        beta = neg ? -nrm2 : nrm2;
         if constexpr (S::cplx) { tauv.x = (beta - alpha.x) / beta; tauv.y = -alpha.y / beta; }
         else tauv = (beta - alpha) / beta;
         scale = Q::recip(S::sub(alpha, S::from_real(beta)));
       }
-      s_scale = scale; s_tauc = S::conj(tauv);
+      s_scale = scale; s_tauc = S::conj(tauv); s_beta = S::from_real(beta);
       if (blockIdx.x == 0) tau[j] = tauv;
-      s_tot[0] = S::from_real(beta);
     }
     __syncthreads();
     const T scale = s_scale, tauc = s_tauc;
     const bool identity = S::is_zero(tauc);
-    // ---- pass 2: v, and H^H applied to the leaf columns right of j
-    for (int r = gtid; r < Mp; r += gsz) {
-      if (r < j) continue;
-      T v;
-      if (r == j) { v = S::one(); A[(size_t)r + (size_t)j * lda] = s_tot[0]; }
-      else {
-        if (identity) continue;
-        v = S::mul(A[(size_t)r + (size_t)j * lda], scale);
-        A[(size_t)r + (size_t)j * lda] = v;
-      }
-      if (identity) continue;
+    // w_c = A(j,c) + conj(scale) * sum conj(x) A(:,c), premultiplied by conj(tau)
+    T tw[QR_CPG];
 #pragma unroll
-      for (int c = 0; c < QR_W; c++) {
-        if (c > j && c < w) {
-          // w_c = A(j,c) + conj(scale) * sum conj(x) A(:,c);  A(r,c) -= conj(tau) * w_c * v_r
-          const T wc = S::add(drow[(size_t)j * QR_W + c], S::mul(S::conj(scale), s_tot[1 + c]));
-          T* p = A + (size_t)r + (size_t)c * lda;
-          *p = S::sub(*p, S::mul(S::mul(tauc, wc), v));
-        }
+    for (int q = 0; q < QR_CPG; q++) {
+      tw[q] = S::zero();
+      if (c0 + q > j && c0 + q < w && !identity)
+        tw[q] = S::mul(tauc, S::add(drow[(size_t)j * QR_W + c0 + q], S::mul(S::conj(scale), s_tot[1 + c0 + q])));
+    }
+    // ---- pass 2: H^H applied to the leaf columns right of j
+    if (!identity) {
+      for (int r = r_first; r < Mp; r += r_step) {
+        if (r < j) continue;
+        const T v = (r == j) ? S::one() : S::mul(A[(size_t)r + (size_t)j * lda], scale);
+#pragma unroll
+        for (int q = 0; q < QR_CPG; q++)
+          if (c0 + q > j && c0 + q < w) {
+            T* p = A + (size_t)r + (size_t)(c0 + q) * lda;
+            *p = S::sub(*p, S::mul(tw[q], v));
+          }
       }
     }
-    __syncthreads();      // s_tot / s_scale are rewritten in the next column
+    __syncthreads();      // every warp has read column j: now it may be overwritten by v (and beta)
+    if (cg == 0) {
+      for (int r = r_first; r < Mp; r += r_step) {
+        if (r < j) continue;
+        T* p = A + (size_t)r + (size_t)j * lda;
+        if (r == j) *p = s_beta;
+        else if (!identity) *p = S::mul(*p, scale);
+      }
+    }
+    // (s_red / s_tot / s_scale are rewritten only after the next column's barriers)
   }
 }
 
@@ -231,7 +251,7 @@ int qr_grid_for(int Mp) {
     AB_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ab_dev()));
     c = std::min(QR_MAXG, std::max(1, sms - 16));     // one CTA per SM at most: co-resident on an otherwise idle device
   }
-  return std::max(1, std::min(c, (Mp + QR_TH * 4 - 1) / (QR_TH * 4)));
+  return std::max(1, std::min(c, (Mp + QR_ROWS - 1) / QR_ROWS));
 }
 
 template <typename T>

@@ -100,6 +100,12 @@ def main():
                 info = ab.clapack_dpotrf(ab.CblasColMajor, uplo, n, W.copy_(S0), n)
                 fl = float(n) ** 3 / 3 + float(n) ** 2 / 2
                 emit(kind="dpotrf", n=n, uplo=uplo, ms=round(ms, 3), tflops=round(fl / ms * 1e-9, 3), info=info)
+            if n <= 16384:                 # QR: flops 2 M N^2 - 2/3 N^3 (qrtst's count for M >= N)
+                tau = torch.zeros(n, dtype=torch.float64, device=dev)
+                ab.reset_launch_count()
+                ms = timeit(lambda: ab.clapack_dgeqrf(ab.CblasColMajor, n, n, W, n, tau), 2, setup=lambda: W.copy_(A0))
+                fl = 2.0 * n * float(n) ** 2 - 2.0 / 3.0 * float(n) ** 3
+                emit(kind="dgeqrf", n=n, ms=round(ms, 3), tflops=round(fl / ms * 1e-9, 3), launches=ab.launch_count() // 3)
             del A0, W, S0
 
 
