@@ -157,12 +157,12 @@ __device__ __forceinline__ unsigned my_smid() { unsigned s; asm volatile("mov.u3
 // GEMM leaves one GPC's worth of SMs to the panel kernels (a thread-block cluster needs all its
 // SMs free inside one GPC; a grid that is merely capped leaves scattered SMs and the cluster
 // would wait for the GEMM to finish - measured with tools/cluster_coexist_test.cu).
-template <bool A_KMAJOR, bool B_KMAJOR, int NI>
+template <bool A_KMAJOR, bool B_KMAJOR, int NI, bool SPLIT>
 __global__ void __launch_bounds__(THREADS, 1)
 dgemm_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                  double* __restrict__ C, size_t ldc, int M, int N, int K, double alpha, double beta,
                  int cmode, int tiles_m, int tiles_n, const int* abort_flag,
-                 const SmMask reserved, int* tile_counter, int ksplit, int Ks, double* __restrict__ Wsplit) {
+                 const SmMask reserved, int* tile_counter, int ksplit, int Ks, double* __restrict__ Wsplit, int sk_per) {
   if (abort_flag && *abort_flag) return;  // POTRF stop-at-first-failure (uniform for the whole grid)
   {
     const unsigned sm = my_smid();
@@ -170,6 +170,9 @@ dgemm_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   }
   constexpr int BN = TileN<NI>::BN, B_TILE_BYTES = TileN<NI>::B_TILE_BYTES, STAGE_BYTES = TileN<NI>::STAGE_BYTES;
   (void)B_TILE_BYTES;
+  // SPLIT = false is the plain kernel (every large GEMM, the whole LU / Cholesky): the split-K / stream-K bookkeeping below
+  // folds away at compile time, so the hot instantiation carries none of its registers.
+  if constexpr (!SPLIT) { ksplit = 1; Ks = 0; sk_per = 0; }
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t bar_base = smem_base + STAGES * STAGE_BYTES;  // full[s] at +8s, empty[s] at +8(STAGES+s)
@@ -191,14 +194,25 @@ dgemm_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   const int mn_tiles = tiles_m * tiles_n;
   const int ntiles = mn_tiles * ksplit;
   auto kt_of = [&](int q) { return ksplit > 1 ? (min(K, (q + 1) * Ks) - q * Ks + BK - 1) / BK : (K + BK - 1) / BK; };
+  // stream-K (sk_per > 0, see launch()): the mn_tiles * KT k-steps of the whole problem are dealt to the CTAs in contiguous
+  // runs of sk_per >= KT steps, so every SM works for the same time whatever the tile count.  A run is cut into segments at
+  // tile boundaries; a tile that a run boundary cuts in two gets its head from CTA b (-> Wsplit slot 2b) and its tail from
+  // CTA b+1 (-> slot 2b+1), and streamk_fixup_kernel adds head + tail in that order: schedule-independent results.
+  const int KTfull = (K + BK - 1) / BK;
+  const int sk_begin = (int)blockIdx.x * sk_per;                       // (launch() keeps the step count below 2^31)
+  const int sk_end = sk_per > 0 ? min(mn_tiles * KTfull, sk_begin + sk_per) : 0;
 
   if (warp == CONS_WARPS) {
     // ===================== TMA producer warp =====================
     uint32_t it = 0;   // running stage counter across tiles
     int next_static = blockIdx.x;
+    int sk_cur = sk_begin;
     for (;;) {
-      int tile;
-      if (tile_counter) { tile = (lane == 0) ? atomicAdd(tile_counter, 1) : 0; tile = __shfl_sync(0xffffffffu, tile, 0); }
+      int tile, sk_kt0 = 0, sk_nk = 0;
+      if (sk_per > 0) {
+        if (sk_cur >= sk_end) tile = ntiles;
+        else { tile = sk_cur / KTfull; sk_kt0 = sk_cur - tile * KTfull; sk_nk = min(KTfull - sk_kt0, sk_end - sk_cur); sk_cur += sk_nk; }
+      } else if (tile_counter) { tile = (lane == 0) ? atomicAdd(tile_counter, 1) : 0; tile = __shfl_sync(0xffffffffu, tile, 0); }
       else { tile = next_static; next_static += gridDim.x; }
       const bool done = tile >= ntiles;
       int m0 = 0, n0 = 0;
@@ -207,8 +221,8 @@ dgemm_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         tile_coords<BN>(tile - q * mn_tiles, tiles_m, tiles_n, m0, n0);
         if (tile_skipped<BN>(cmode, m0, n0)) continue;
       }
-      const int kbeg = q * Ks;                 // 0 without split-K (Ks = 0)
-      const int nk = done ? 1 : kt_of(q);
+      const int kbeg = sk_per > 0 ? sk_kt0 * BK : q * Ks;                 // 0 without split-K (Ks = 0)
+      const int nk = done ? 1 : (sk_per > 0 ? sk_nk : kt_of(q));
       for (int kt = 0; kt < nk; kt++, it++) {
         const uint32_t s = it % STAGES;
         const uint32_t ph = (it / STAGES) & 1;
@@ -243,6 +257,7 @@ dgemm_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   const uint32_t zero_rt = (uint32_t)(ldc >> 63);   // 0 at run time, unknown to the compiler (see mbar_release)
 
   uint32_t it = 0;
+  int sk_ccur = sk_begin;
   for (;;) {
     // the first stage of a tile carries the tile index (or the end marker)
     {
@@ -255,9 +270,17 @@ dgemm_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     int m0, n0;
     const int q = tile / mn_tiles;
     tile_coords<BN>(tile - q * mn_tiles, tiles_m, tiles_n, m0, n0);
-    const int KT = kt_of(q);
+    int KT = kt_of(q);
+    int sk_slot = -1;                 // >= 0: this segment is part of a tile that a run boundary cuts
+    if (sk_per > 0) {
+      const int kt0 = sk_ccur - tile * KTfull;
+      KT = min(KTfull - kt0, sk_end - sk_ccur);
+      sk_ccur += KT;
+      if (kt0 > 0) sk_slot = 2 * ((int)blockIdx.x - 1) + 1;          // tail of the tile the previous CTA started
+      else if (KT < KTfull) sk_slot = 2 * (int)blockIdx.x;          // head of the tile the next CTA finishes
+    }
 
-    if (!beta0 && ksplit == 1) {
+    if (!beta0 && ksplit == 1 && sk_slot < 0) {
       // bring this tile's C block (128 columns x 1 KiB) into L2 while the k loop runs: thread i of
       // the 256 consumers takes column i/2, half i%2, four 128-byte lines
       const int ctid = (int)threadIdx.x;               // consumer warps are 0..7
@@ -330,6 +353,19 @@ dgemm_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     // fit: 3 of the 9 warps share a 16K-register sub-partition, which caps the kernel at 168
     // registers, 128 of them accumulators).  The rounds hit L2 because the C block was prefetched
     // at the start of the tile; from DRAM they cost 9.6 us per tile, 12 % of a K=512 update.
+    if (sk_slot >= 0) {        // stream-K: dense BM x BN partial tile (rows / columns past the matrix edge hold zeros)
+      double* W = Wsplit + (size_t)sk_slot * BM * BN;
+#pragma unroll
+      for (int ni = 0; ni < NI; ni++) {
+#pragma unroll
+        for (int e = 0; e < 2; e++) {
+          const int nl = wn * 8 * NI + ni * 8 + 2 * t + e;
+#pragma unroll
+          for (int mi = 0; mi < 8; mi++) W[(size_t)nl * BM + wm * 64 + mi * 8 + g] = acc[mi][ni][e];
+        }
+      }
+      continue;
+    }
     if (ksplit > 1) {          // partial product of slice q, as computed (alpha and beta belong to the reduction)
       double* W = Wsplit + (size_t)q * M * N;
 #pragma unroll
@@ -435,18 +471,65 @@ __global__ void __launch_bounds__(256) splitk_reduce_kernel(int M, int N, int ks
   }
 }
 
+// stream-K second pass: run boundary b (between CTA b and b+1) at step (b+1)*per; if it falls inside a tile, that tile is
+// head (slot 2b) + tail (slot 2b+1):  C <- alpha * (head + tail) + beta * C
+template <int NI>
+__global__ void __launch_bounds__(256) streamk_fixup_kernel(int M, int N, int KTfull, int tiles_m, int tiles_n, int per, const double* __restrict__ W,
+                                                             double alpha, double beta, double* __restrict__ C, size_t ldc) {
+  constexpr int BN = TileN<NI>::BN;
+  const long long cut = (long long)(blockIdx.x + 1) * per;
+  if (cut >= (long long)tiles_m * tiles_n * KTfull || cut % KTfull == 0) return;
+  const int tile = (int)(cut / KTfull);
+  int m0, n0;
+  tile_coords<BN>(tile, tiles_m, tiles_n, m0, n0);
+  const double* head = W + (size_t)(2 * blockIdx.x) * BM * BN;
+  const double* tail = head + (size_t)BM * BN;
+  for (int idx = threadIdx.x; idx < BM * BN; idx += blockDim.x) {
+    const int ml = idx % BM, nl = idx / BM;
+    const int m = m0 + ml, n = n0 + nl;
+    if (m >= M || n >= N) continue;
+    const double s = head[idx] + tail[idx];
+    double* c = C + (size_t)n * ldc + m;
+    *c = (beta == 0.) ? alpha * s : alpha * s + beta * *c;
+  }
+}
+
 constexpr int NCOUNTERS = 8192;
 
 template <bool AK, bool BK_, int NI>
 void launch(const CUtensorMap& ta, const CUtensorMap& tb, double* C, size_t ldc, int M, int N, int K, double alpha,
-            double beta, int cmode, const int* abort_flag, int ksplit = 1) {
+            double beta, int cmode, const int* abort_flag, int ksplit = 1, bool streamk = false) {
   constexpr int smem_req = TileN<NI>::SMEM_BYTES, BN = TileN<NI>::BN;
   static PerDeviceOnce attr_once;
-  attr_once([] { AB_CUDA_CHECK(cudaFuncSetAttribute(dgemm_tma_kernel<AK, BK_, NI>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_req)); });
+  attr_once([] {
+    AB_CUDA_CHECK(cudaFuncSetAttribute(dgemm_tma_kernel<AK, BK_, NI, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_req));
+    AB_CUDA_CHECK(cudaFuncSetAttribute(dgemm_tma_kernel<AK, BK_, NI, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_req));
+  });
   const int tiles_m = (M + BM - 1) / BM, tiles_n = (N + BN - 1) / BN;
   int grid = std::min(tiles_m * tiles_n, gemm_cta_cap());
   SmMask mask = {{0, 0, 0, 0}};
   int* counter = nullptr;
+  if (streamk) {
+    const int KTfull = (K + BK - 1) / BK;
+    const int G = gemm_cta_cap();
+    const long long total = (long long)tiles_m * tiles_n * KTfull;
+    const int per = (int)((total + G - 1) / G);
+    if (per >= KTfull && total + per < 0x7fffffffLL) {
+      double* W = nullptr;
+      cudaStream_t st = current_stream();
+      keep_pool_cached();
+      AB_CUDA_CHECK(cudaMallocAsync(reinterpret_cast<void**>(&W), sizeof(double) * 2 * (size_t)G * BM * BN, st));
+      dgemm_tma_kernel<AK, BK_, NI, true><<<G, THREADS, smem_req, st>>>(ta, tb, C, ldc, M, N, K, alpha, beta, C_FULL, tiles_m, tiles_n, abort_flag,
+                                                                 mask, counter, 1, 0, W, per);
+      count_launch();
+      AB_CUDA_CHECK(cudaGetLastError());
+      streamk_fixup_kernel<NI><<<G - 1, 256, 0, st>>>(M, N, KTfull, tiles_m, tiles_n, per, W, alpha, beta, C, ldc);
+      count_launch();
+      AB_CUDA_CHECK(cudaGetLastError());
+      AB_CUDA_CHECK(cudaFreeAsync(W, st));
+      return;
+    }
+  }
   if (ksplit > 1) {
     // small problem: the k range is cut into ksplit slices so that every SM has work; partial products go to a stream-ordered
     // scratch buffer and are added in a fixed order (the reference's ammm_tN / ammm_IP special cases split long-K small-C
@@ -458,8 +541,8 @@ void launch(const CUtensorMap& ta, const CUtensorMap& tb, double* C, size_t ldc,
     keep_pool_cached();
     AB_CUDA_CHECK(cudaMallocAsync(reinterpret_cast<void**>(&W), sizeof(double) * (size_t)M * N * ksplit, st));
     grid = std::min(tiles_m * tiles_n * ksplit, gemm_cta_cap());
-    dgemm_tma_kernel<AK, BK_, NI><<<grid, THREADS, smem_req, st>>>(ta, tb, C, ldc, M, N, K, 1.0, 0.0, C_FULL, tiles_m, tiles_n, abort_flag,
-                                                                   mask, counter, ksplit, Ks, W);
+    dgemm_tma_kernel<AK, BK_, NI, true><<<grid, THREADS, smem_req, st>>>(ta, tb, C, ldc, M, N, K, 1.0, 0.0, C_FULL, tiles_m, tiles_n, abort_flag,
+                                                                   mask, counter, ksplit, Ks, W, 0);
     count_launch();
     AB_CUDA_CHECK(cudaGetLastError());
     const size_t total = (size_t)M * N;
@@ -479,8 +562,8 @@ void launch(const CUtensorMap& ta, const CUtensorMap& tb, double* C, size_t ldc,
     counter = ring + (g_counter_next++ % NCOUNTERS);
     AB_CUDA_CHECK(cudaMemsetAsync(counter, 0, sizeof(int), current_stream()));
   }
-  dgemm_tma_kernel<AK, BK_, NI><<<grid, THREADS, smem_req, current_stream()>>>(
-      ta, tb, C, ldc, M, N, K, alpha, beta, cmode, tiles_m, tiles_n, abort_flag, mask, counter, 1, 0, nullptr);
+  dgemm_tma_kernel<AK, BK_, NI, false><<<grid, THREADS, smem_req, current_stream()>>>(
+      ta, tb, C, ldc, M, N, K, alpha, beta, cmode, tiles_m, tiles_n, abort_flag, mask, counter, 1, 0, nullptr, 0);
   count_launch();
   AB_CUDA_CHECK(cudaGetLastError());
 }
@@ -499,9 +582,10 @@ int pick_ni(int M, int N) {
 // streams together - measured: DGETRF N=16384 137 -> 147 ms): minimise  rounds x (time of one work item)  +  reduction pass, with the measured
 // 244 GFLOP/s per SM, ~2 us to fill the stage ring per work item and ~3 TB/s for the reduction.  Only plain GEMMs (full C,
 // no SM reservation) are split; a split never leaves fewer than 64 k per slice.
-void pick_shape(int M, int N, int K, int cmode, int& ni, int& ksplit) {
+void pick_shape(int M, int N, int K, int cmode, int& ni, int& ksplit, bool& streamk) {
   ni = pick_ni(M, N);
   ksplit = 1;
+  streamk = false;
   static const int on = [] { const char* v = getenv("ATLB200_GEMM_SPLITK"); return v ? atoi(v) : 1; }();
   if (!on || !g_splitk_ok || cmode != C_FULL || g_reserved_on || K < 128) return;
   const int cap = gemm_cta_cap();
@@ -520,7 +604,13 @@ void pick_shape(int M, int N, int K, int cmode, int& ni, int& ksplit) {
       const double item = 2.0 * BM * bn * ((double)K / ks) / 244e9 + 2e-6;
       const double red = ks > 1 ? 6e-6 + (double)(ks + 2) * M * N * 8 / 3e12 : 0.0;
       const double t = rounds * item + red;
-      if (t < best * 0.97) { best = t; ni = cand_ni; ksplit = ks; }
+      if (t < best * 0.97) { best = t; ni = cand_ni; ksplit = ks; streamk = false; }
+    }
+    // stream-K: every SM gets total / cap k-steps (needs at least one whole tile's worth per SM)
+    static const int sk_on = [] { const char* v = getenv("ATLB200_GEMM_STREAMK"); return v ? atoi(v) : 1; }();
+    if (sk_on && tiles >= cap) {
+      const double t = (double)tiles / cap * (2.0 * BM * bn * (double)K / 244e9) + 4e-6 + 8e-6 + 3.0 * cap * BM * bn * 8 / 3e12;
+      if (t < best * 0.97) { best = t; ni = cand_ni; ksplit = 1; streamk = true; }
     }
   }
 }
@@ -560,15 +650,16 @@ bool dgemm_tma(int ta, int tb, int M, int N, int K, double alpha, const double* 
   CUtensorMap mA, mB;
   bool ok;
   int ni, ksplit;
-  pick_shape(M, N, K, cmode, ni, ksplit);
+  bool streamk;
+  pick_shape(M, N, K, cmode, ni, ksplit, streamk);
   // op(A) is M x K.  ta: stored K x M (k contiguous, K-major) else stored M x K (m contiguous).
   ok = ta ? make_map(&mA, A, K, M, lda, BK, BM) : make_map(&mA, A, M, K, lda, 16, BK);
   if (!ok) return false;
   // op(B) is K x N.  !tb: stored K x N (K-major) else stored N x K (n contiguous).
   ok = tb ? make_map(&mB, B, N, K, ldb, 16, BK) : make_map(&mB, B, K, N, ldb, BK, 32 * ni);
   if (!ok) return false;
-#define AB_GO(AK, BKM) do { if (ni == 2) launch<AK, BKM, 2>(mA, mB, C, ldc, M, N, K, alpha, beta, cmode, abort_flag, ksplit); \
-                            else launch<AK, BKM, 4>(mA, mB, C, ldc, M, N, K, alpha, beta, cmode, abort_flag, ksplit); } while (0)
+#define AB_GO(AK, BKM) do { if (ni == 2) launch<AK, BKM, 2>(mA, mB, C, ldc, M, N, K, alpha, beta, cmode, abort_flag, ksplit, streamk); \
+                            else launch<AK, BKM, 4>(mA, mB, C, ldc, M, N, K, alpha, beta, cmode, abort_flag, ksplit, streamk); } while (0)
   if (ta) { if (!tb) AB_GO(true, true); else AB_GO(true, false); }
   else    { if (!tb) AB_GO(false, true); else AB_GO(false, false); }
 #undef AB_GO

@@ -71,3 +71,27 @@ def test_fuzz_syrk_trsm(oracle, pre):
         ab.cblas_trsm(pre, ColMajor, side, uplo, ta, diag, M, N, cases.scal(pre, 0.7), A, A.shape[0], got, got.shape[0])
         assert _resid(pre, got[:M], want[:M], max(_nrm1(want[:M]), 1), max(M, N)) < 20.0, (pre, it, side, uplo, ta, diag, M, N)
         assert np.array_equal(got[M:], B0[M:])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("M,N,K,ta,tb", [(2000, 2000, 2000, NoTrans, NoTrans), (1900, 2300, 1111, Trans, NoTrans), (2049, 1793, 640, NoTrans, Trans),
+                                         (512, 512, 4096, NoTrans, NoTrans), (130, 70, 9000, Trans, Trans)])
+def test_dgemm_streamk_and_splitk_shapes(M, N, K, ta, tb):
+    """Shapes the DGEMM shape model sends to stream-K (a tile count that is no multiple of the SM count) or split-K (few tiles,
+    long K): tester residual against a float64 matmul, lda/ldc gaps untouched, and bit-identical results run to run (the
+    partial tiles are added in a fixed order)."""
+    rng = np.random.default_rng(M + N + K)
+    ra, ca = (M, K) if ta == NoTrans else (K, M)
+    rb, cb = (K, N) if tb == NoTrans else (N, K)
+    A = np.asfortranarray(rng.random((ra + 2, ca)) - 0.5); B = np.asfortranarray(rng.random((rb + 4, cb)) - 0.5)
+    C0 = np.asfortranarray(rng.random((M + 6, N)) - 0.5)
+    opA = A[:ra] if ta == NoTrans else A[:ra].T
+    opB = B[:rb] if tb == NoTrans else B[:rb].T
+    want = -1.1 * (opA @ opB) + 0.7 * C0[:M]
+    got = C0.copy(order="F"); again = C0.copy(order="F")
+    ab.cblas_dgemm(ColMajor, ta, tb, M, N, K, -1.1, A, ra + 2, B, rb + 4, 0.7, got, M + 6)
+    ab.cblas_dgemm(ColMajor, ta, tb, M, N, K, -1.1, A, ra + 2, B, rb + 4, 0.7, again, M + 6)
+    assert np.array_equal(got, again), "not deterministic"
+    assert np.array_equal(got[M:], C0[M:]), "ldc gap touched"
+    r = _nrm1(got[:M] - want) / (max(_nrm1(opA), 1) * max(_nrm1(opB), 1) * eps_of("d") * K)
+    assert r < 5.0, r
