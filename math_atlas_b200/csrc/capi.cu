@@ -293,6 +293,30 @@ int multi_devices() {
 }  // namespace
 extern "C" void atlb200_set_devices(int n) { g_devices = n < 1 ? 1 : n; }
 
+static void multi_enable_peers(int d, int D) {      // current device = d
+  DevCtx& cx = g_dev[d];
+  if (cx.peers) return;
+  // cudaDeviceEnablePeerAccess covers cudaMalloc memory only; the operands here come from the device's stream-ordered pool,
+  // which needs its own grant - without it every "peer" copy is staged through host memory (measured: the 8-device GEMM ran
+  // slower than one device)
+  cudaMemPool_t pool = nullptr;
+  const bool have_pool = cudaDeviceGetDefaultMemPool(&pool, d) == cudaSuccess;
+  for (int p = 0; p < D; p++) {
+    if (p == d) continue;
+    int can = 0;
+    cudaDeviceCanAccessPeer(&can, d, p);                       // can d map p's memory ...
+    if (can && cudaDeviceEnablePeerAccess(p, 0) != cudaSuccess) (void)cudaGetLastError();
+    int can_rev = 0;
+    cudaDeviceCanAccessPeer(&can_rev, p, d);                   // ... and may p read / write this device's pool
+    if (have_pool && can_rev) {
+      cudaMemAccessDesc desc{};
+      desc.location.type = cudaMemLocationTypeDevice; desc.location.id = p; desc.flags = cudaMemAccessFlagsProtReadWrite;
+      if (cudaMemPoolSetAccess(pool, &desc, 1) != cudaSuccess) (void)cudaGetLastError();
+    }
+  }
+  cx.peers = true;
+}
+
 template <typename T>
 static bool atl_gemm_multi(int TA, int TB, size_t M, size_t N, size_t K, T alpha, const T* A, size_t lda, const T* B, size_t ldb,
                            T beta, T* C, size_t ldc) {
@@ -323,11 +347,7 @@ static bool atl_gemm_multi(int TA, int TB, size_t M, size_t N, size_t K, T alpha
       AB_CUDA_CHECK(cudaStreamCreateWithFlags(&cx.st, cudaStreamNonBlocking));
       AB_CUDA_CHECK(cudaEventCreateWithFlags(&cx.part, cudaEventDisableTiming));
     }
-    if (!cx.peers) {
-      for (int p = 0; p < D; p++)
-        if (p != d) { int can = 0; cudaDeviceCanAccessPeer(&can, d, p); if (can && cudaDeviceEnablePeerAccess(p, 0) != cudaSuccess) (void)cudaGetLastError(); }
-      cx.peers = true;
-    }
+    multi_enable_peers(d, D);
     keep_pool_cached();
     const size_t c0 = std::min(N, per * d), nc = std::min(per, N - c0);
     AB_CUDA_CHECK(cudaMallocAsync(&dA[d], esz * lda_d * ca, cx.st));
@@ -404,14 +424,6 @@ struct LuDev {
 };
 LuDev g_ludev[AB_MAX_DEV];
 }  // namespace
-
-static void multi_enable_peers(int d, int D) {      // current device = d
-  DevCtx& cx = g_dev[d];
-  if (cx.peers) return;
-  for (int p = 0; p < D; p++)
-    if (p != d) { int can = 0; cudaDeviceCanAccessPeer(&can, d, p); if (can && cudaDeviceEnablePeerAccess(p, 0) != cudaSuccess) (void)cudaGetLastError(); }
-  cx.peers = true;
-}
 
 template <typename T>
 static bool atl_getrf_multi(int M, int N, T* A, size_t lda, int* ipiv, int* info_out) {

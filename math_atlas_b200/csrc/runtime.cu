@@ -27,13 +27,15 @@ struct Slots {
       if (ptr[i]) cudaFree(ptr[i]);   // best effort at thread exit (may run after context teardown)
   }
 };
-thread_local Slots g_slots;
+// one table per device: a host thread that drives several GPUs (capi.cu: atl_getrf_multi) must not free and re-allocate a
+// slot - an implicit device synchronisation - every time it switches devices
+thread_local Slots g_slots_dev[AB_MAX_DEV];
 }  // namespace
 
 void* workspace(size_t bytes, int slot) {
-  Slots& s = g_slots;
   int dev = 0;
   AB_CUDA_CHECK(cudaGetDevice(&dev));
+  Slots& s = g_slots_dev[(dev >= 0 && dev < AB_MAX_DEV) ? dev : AB_MAX_DEV - 1];
   if (s.ptr[slot] && s.size[slot] >= bytes && s.dev[slot] == dev) return s.ptr[slot];
   if (s.ptr[slot]) { AB_CUDA_CHECK(cudaFree(s.ptr[slot])); s.ptr[slot] = nullptr; s.size[slot] = 0; }
   size_t want = bytes + bytes / 4 + 4096;
@@ -62,9 +64,11 @@ void keep_pool_cached() {
 }
 
 void free_workspace() {
-  Slots& s = g_slots;
-  for (int i = 0; i < Slots::N; i++)
-    if (s.ptr[i]) { cudaFree(s.ptr[i]); s.ptr[i] = nullptr; s.size[i] = 0; }
+  for (int d = 0; d < AB_MAX_DEV; d++) {
+    Slots& s = g_slots_dev[d];
+    for (int i = 0; i < Slots::N; i++)
+      if (s.ptr[i]) { cudaFree(s.ptr[i]); s.ptr[i] = nullptr; s.size[i] = 0; }
+  }
   // ... and what the stream-ordered pool has cached (staged host operands, packed tensor-core panels)
   int dev = 0;
   cudaMemPool_t pool;
