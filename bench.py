@@ -415,6 +415,27 @@ def run_ours(args):
                   "frac_of_fp64_peak": round(lu_flops / (best * 1e-3) * 1e-12 / (peak * world), 4) if peak else None}
         del loc
 
+    # ---- DGEQRF at the same N (single GPU, device-resident) ----
+    dgeqrf = None
+    if world == 1 and not args.no_getrf:
+        try:
+            Q0 = torch.rand((n, n), device=dev, dtype=torch.float64, generator=gen) - 0.5
+            tau = torch.zeros(n, dtype=torch.float64, device=dev)
+            W = Q0.clone()
+            ab.clapack_dgeqrf(ab.CblasColMajor, n, n, W, n, tau)          # warm-up
+            best = 1e30
+            for _ in range(2):
+                W.copy_(Q0); torch.cuda.synchronize()
+                a0 = torch.cuda.Event(enable_timing=True); a1 = torch.cuda.Event(enable_timing=True)
+                a0.record(); ab.clapack_dgeqrf(ab.CblasColMajor, n, n, W, n, tau); a1.record(); torch.cuda.synchronize()
+                best = min(best, a0.elapsed_time(a1))
+            qr_flops = 2.0 * n * float(n) ** 2 - 2.0 / 3.0 * float(n) ** 3            # M >= N Householder QR
+            dgeqrf = {"metric": f"dgeqrf_gflops_n{n}", "value": round(qr_flops / (best * 1e-3) * 1e-9, 2), "unit": UNIT, "ms": round(best, 3),
+                      "frac_of_fp64_peak": round(qr_flops / (best * 1e-3) * 1e-12 / peak, 4) if peak else None}
+            del Q0, W, tau
+        except Exception as e:      # an extra key must never cost the headline line
+            dgeqrf = {"error": repr(e)}
+
     # ---- BASELINE configs 4 and 5: DPOTRF / DGETRF N = 65536 on 1/2/4/8 GPUs (driver-measured) ----
     big = None
     if not args.no_big:
@@ -471,6 +492,8 @@ def run_ours(args):
         line["cpu_baseline"] = cpu
     if dgetrf is not None:
         line["dgetrf"] = dgetrf
+    if dgeqrf is not None:
+        line["dgeqrf"] = dgeqrf
     if big:
         for kname, v in big.items():
             if peak and isinstance(v, dict) and v.get("value"):
