@@ -10,13 +10,14 @@
 //     a fixed order, and a second pass forms v = x / (alpha - beta) and applies H^H to the leaf - a thread only ever
 //     re-reads the rows it wrote itself, so one barrier per column suffices (larfg + larf of geqr2 fused);
 //   * 128-column block: after each leaf its block reflector is applied to the rest of the block, then ONE block reflector
-//     for the whole block (T built from V^H V, larft) updates the trailing matrix with three GEMM-shaped calls (larfb):
-//     W = V^H C (DGEMM, K = rows), W = T^H W (TRMM), C -= V W (DGEMM, K = 128).
+//     for the whole block updates the trailing matrix with three calls (larfb): W = V^H C (DGEMM, K = rows), W = T^H W as a
+//     triangular solve with T^-1 = triu(V^H V) + diag(1/tau) (no larft recurrence, see qr_tinv_kernel), C -= V W (DGEMM, K = 128).
 // Differences to LAPACK's xLARFG that a caller could see: the norm is sqrt(sum |x|^2) without the scaled accumulation of
 // xNRM2 and without the re-scaling loop for |beta| < safmin (inputs with entries near the under/overflow thresholds).
 #include "ab_api.h"
 #include "dgemm_tma.h"
 #include <cfloat>
+#include <cstdlib>
 #include <algorithm>
 
 namespace ab {
@@ -146,11 +147,15 @@ geqr2_panel_kernel(int Mp, int w, T* A, size_t lda, T* tau, T* part, T* drow, un
     __syncthreads();
     if (tid <= QR_W) part[((size_t)j * G + blockIdx.x) * (QR_W + 1) + tid] = S::add(s_red[0][tid], s_red[1][tid]);
     qr_grid_barrier(counter, (unsigned)G * (unsigned)(j + 1));
-    // ---- every CTA adds the G partial results in the same order
-    if (tid <= QR_W) {
-      T v = S::zero();
-      for (int g = 0; g < G; g++) v = S::add(v, part[((size_t)j * G + g) * (QR_W + 1) + tid]);
-      s_tot[tid] = v;
+    // ---- every CTA adds the G partial results in the same (fixed) order: warp q takes the values q, q+8, ...; a lane adds the
+    //      CTAs lane, lane+32, ... and the lanes are combined by the same shuffle tree everywhere (bit-identical in every CTA,
+    //      which the redundant larfg below relies on; one warp per value instead of one thread: 3.2 -> 0.6 us per column)
+    for (int v = wid; v <= QR_W; v += QR_TH / 32) {
+      T sum = S::zero();
+      for (int g = lane; g < G; g += 32) sum = S::add(sum, part[((size_t)j * G + g) * (QR_W + 1) + v]);
+#pragma unroll
+      for (int off = 16; off > 0; off >>= 1) sum = S::add(sum, qr_shfl_xor<T>(sum, off));
+      if (lane == 0) s_tot[v] = sum;
     }
     __syncthreads();
     if (tid == 0) {
@@ -217,27 +222,24 @@ __global__ void qr_copy_v_kernel(int Mp, int nb, const T* A, size_t lda, T* V, s
   V[(size_t)r + (size_t)c * ldv] = r > c ? A[(size_t)r + (size_t)c * lda] : (r == c ? S::one() : S::zero());
 }
 
-// larft, forward / columnwise (qr.base:3730 ff.): T(i,i) = tau_i, T(0:i, i) = -tau_i * T(0:i,0:i) * G(0:i, i) with G = V^H V.
-// One CTA; column i needs the finished columns < i.  Below the diagonal T is zero.
+// The triangular factor of the block reflector H = I - V T V^H is never formed: H unitary means T^-1 + T^-H = V^H V, so T^-1 is
+// the upper triangle of G = V^H V with 1 / tau_i on the diagonal (2 Re(1/tau_i) = |v_i|^2 holds for LAPACK's real and complex
+// tau alike), and "W <- T^H W" of larfb (qr.base:2085 ff.) becomes the triangular SOLVE Tinv^H Y = W.  This replaces the
+// reference's larft recurrence (qr.base:3730 ff.; one CTA, a chain of nb dependent steps: 19 % of the kernel time of the first
+// version) by an element-wise kernel.  tau_i = 0 (H_i = I): a huge diagonal entry makes row / column i of T vanish to rounding.
 template <typename T>
-__global__ void __launch_bounds__(128) qr_larft_kernel(int nb, const T* tau, const T* G, int ldg, T* Tm, int ldt) {
+__global__ void qr_tinv_kernel(int nb, const T* tau, const T* G, int ldg, T* Ti, int ldt) {
   using S = ST<T>;
-  extern __shared__ __align__(16) unsigned char qr_smem[];
-  T* Ts = reinterpret_cast<T*>(qr_smem);           // upper triangle, packed by columns: (a, b), a <= b, at b(b+1)/2 + a
-  const int a = threadIdx.x;
-  for (int i = 0; i < nb; i++) {
-    const T ti = tau[i];
-    if (a < i) {
-      T s = S::zero();
-      for (int b = a; b < i; b++) S::fma(s, Ts[b * (b + 1) / 2 + a], G[b + (size_t)i * ldg]);
-      Ts[i * (i + 1) / 2 + a] = S::mul(S::sub(S::zero(), ti), s);
-    } else if (a == i) Ts[i * (i + 1) / 2 + a] = ti;
-    __syncthreads();
+  using R = typename S::real;
+  const int a = blockIdx.x * blockDim.x + threadIdx.x, i = blockIdx.y;
+  if (a >= nb || i >= nb) return;
+  T v = S::zero();
+  if (a < i) v = G[a + (size_t)i * ldg];
+  else if (a == i) {
+    const T t = tau[i];
+    v = S::is_zero(t) ? S::from_real(sizeof(R) == 4 ? (R)1e30 : (R)1e300) : QrMath<T>::recip(t);
   }
-  for (int idx = a; idx < nb * nb; idx += blockDim.x) {
-    const int r = idx % nb, c = idx / nb;
-    Tm[r + (size_t)c * ldt] = r <= c ? Ts[c * (c + 1) / 2 + r] : S::zero();
-  }
+  Ti[a + (size_t)i * ldt] = v;
 }
 
 struct QrScratch { unsigned* counter = nullptr; void* part = nullptr; void* drow = nullptr; size_t part_bytes = 0; int dev = -1; };
@@ -249,7 +251,8 @@ int qr_grid_for(int Mp) {
   if (!c) {
     int sms = 0;
     AB_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ab_dev()));
-    c = std::min(QR_MAXG, std::max(1, sms - 16));     // one CTA per SM at most: co-resident on an otherwise idle device
+    static const int env_g = [] { const char* v = getenv("ATLB200_QR_MAXG"); return v ? atoi(v) : 0; }();   // experiments: smaller leaf grid
+    c = std::min(env_g > 0 ? std::min(env_g, QR_MAXG) : QR_MAXG, std::max(1, sms - 16));     // one CTA per SM at most: co-resident on an otherwise idle device
   }
   return std::max(1, std::min(c, (Mp + QR_ROWS - 1) / QR_ROWS));
 }
@@ -275,18 +278,18 @@ void qr_leaf(int Mp, int w, T* A, size_t lda, T* tau) {
   AB_CUDA_CHECK(cudaGetLastError());
 }
 
-// C (Mp x n) <- (I - V T^H V^H) C with V = Vw (Mp x nb, explicit), T nb x nb upper; W: nb x n scratch
+// C (Mp x n) <- (I - V T^H V^H) C with V = Vw (Mp x nb, explicit), Tm = T^-1 (nb x nb upper); W: nb x n scratch
 template <typename T>
 void qr_larfb(int Mp, int n, int nb, const T* Vw, size_t ldv, const T* Tm, int ldt, T* C, size_t ldc, T* W) {
   using S = ST<T>;
   if (n <= 0 || Mp <= 0) return;
   const int ct = S::cplx ? ConjTrans : TransT;
   gemm<T>(ct, NoTrans, nb, n, Mp, S::one(), Vw, ldv, C, ldc, S::zero(), W, (size_t)nb);
-  trmm<T>(Left, Upper, ct, NonUnit, nb, n, S::one(), Tm, (size_t)ldt, W, (size_t)nb);
+  trsm<T>(Left, Upper, ct, NonUnit, nb, n, S::one(), Tm, (size_t)ldt, W, (size_t)nb);          // Tm holds T^-1: W <- T^H W
   gemm<T>(NoTrans, NoTrans, Mp, n, nb, S::from_real(-1), Vw, ldv, W, (size_t)nb, S::one(), C, ldc);
 }
 
-// explicit V and T of the nb factored columns at A (Mp rows)
+// explicit V and T^-1 of the nb factored columns at A (Mp rows)
 template <typename T>
 void qr_build_vt(int Mp, int nb, const T* A, size_t lda, const T* tau, T* Vw, size_t ldv, T* G, T* Tm) {
   using S = ST<T>;
@@ -295,7 +298,7 @@ void qr_build_vt(int Mp, int nb, const T* A, size_t lda, const T* tau, T* Vw, si
   count_launch();
   const int ct = S::cplx ? ConjTrans : TransT;
   gemm<T>(ct, NoTrans, nb, nb, Mp, S::one(), Vw, ldv, Vw, ldv, S::zero(), G, (size_t)nb);
-  qr_larft_kernel<T><<<1, 128, sizeof(T) * nb * (nb + 1) / 2, st>>>(nb, tau, G, nb, Tm, nb);
+  qr_tinv_kernel<T><<<dim3((nb + 63) / 64, nb), 64, 0, st>>>(nb, tau, G, nb, Tm, nb);
   count_launch();
   AB_CUDA_CHECK(cudaGetLastError());
 }
@@ -306,8 +309,6 @@ template <typename T>
 void geqrf(int M, int N, T* A, size_t lda, T* tau) {
   const int MN = std::min(M, N);
   if (MN <= 0) return;
-  static PerDeviceOnce attr_once;
-  attr_once([] { AB_CUDA_CHECK(cudaFuncSetAttribute(qr_larft_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(T) * QR_NB * (QR_NB + 1) / 2))); });
   const size_t ldv = ((size_t)M + 15) & ~(size_t)15;
   // scratch: V (ldv x NB), W (NB x N), G and T (NB x NB each)
   T* Vw = static_cast<T*>(workspace(sizeof(T) * (ldv * QR_NB + (size_t)QR_NB * N + 2 * QR_NB * QR_NB), 6));
