@@ -583,7 +583,10 @@ static long cluster_capacity() { return (long)cluster_max_size<T, W, RPT>() * CL
 template <typename T, int W, int RPT>
 static void cluster_launch(int M, int w, T* A, size_t lda, int* d_ipiv, int* d_info, int piv_off, int info_off) {
   const int need = (M + CL_TPB * RPT - 1) / (CL_TPB * RPT);
-  int c = 1;
+  // at least two CTAs: the async leaf pushes its candidates with st.async into shared::cluster addresses, which
+  // compute-sanitizer (memcheck: "Cluster needs to have at least 2 blocks") rejects for a cluster of one - the second CTA of
+  // a short panel owns no rows and only takes part in the exchange
+  int c = 2;
   while (c < need) c <<= 1;
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(c); cfg.blockDim = dim3(CL_TPB); cfg.dynamicSmemBytes = 0; cfg.stream = current_stream();
