@@ -100,6 +100,15 @@ def test_clapack_argument_errors_return_negative(L, pre):
     assert ab.clapack_potrf(pre, 102, 0, 4, buf, 4) == -2
     assert ab.clapack_potrf(pre, 102, 121, -1, buf, 4) == -3
     assert ab.clapack_potrf(pre, 102, 121, 4, buf, 3) == -5
+    # QR: argument numbering of the reference's clapack_Xgeqrf (Clint/atlas-clp.base:551-585: lda is argument 5)
+    tau = np.zeros(8, dtype=np.complex128)
+    assert ab.clapack_geqrf(pre, 0, 4, 4, buf, 4, tau) == -1
+    assert ab.clapack_geqrf(pre, 102, -1, 4, buf, 4, tau) == -2
+    assert ab.clapack_geqrf(pre, 102, 4, -1, buf, 4, tau) == -3
+    assert ab.clapack_geqrf(pre, 102, 4, 4, buf, 3, tau) == -5
+    assert ab.clapack_geqrf(pre, 101, 3, 5, buf, 4, tau) == -5     # row-major: lda >= N
+    assert ab.last_xerbla() == (5, f"clapack_{pre}geqrf")
+    assert ab.clapack_geqrf(pre, 102, 0, 0, buf, 1, tau) == 0      # quick return, nothing referenced
     ab.last_xerbla()
 
 
@@ -111,6 +120,24 @@ def test_quick_returns_need_no_device(L):
     assert ab.clapack_dgetrf(102, 0, 0, buf, 1, np.zeros(1, dtype=np.int32)) == 0
     assert ab.clapack_dpotrf(102, 121, 0, buf, 1) == 0
     assert ab.last_xerbla()[0] == 0
+
+
+def test_f77_geqrf_argument_errors_and_workspace_query(L):
+    """dgeqrf_: LAPACK's argument numbering (info = -i, xerbla_ called), LWORK = -1 answers in WORK(1) without touching A"""
+    import ctypes as C
+    a = np.zeros(16); tau = np.zeros(4); work = np.zeros(4)
+
+    def call(m, n, lda, lwork):
+        v = [C.c_int(x) for x in (m, n, lda, lwork, 99)]
+        L.dgeqrf_(C.byref(v[0]), C.byref(v[1]), C.c_void_p(a.ctypes.data), C.byref(v[2]), C.c_void_p(tau.ctypes.data), C.c_void_p(work.ctypes.data),
+                  C.byref(v[3]), C.byref(v[4]))
+        return v[4].value
+    assert call(-1, 4, 4, 4) == -1
+    assert call(4, -1, 4, 4) == -2
+    assert call(4, 4, 3, 4) == -4
+    assert call(4, 4, 4, 2) == -7
+    ab.last_xerbla()
+    assert call(4, 4, 4, -1) == 0 and work[0] >= 4 and not a.any()
 
 
 def test_f77_argument_errors(L):
