@@ -14,9 +14,10 @@ e2e     = the same call through the C ABI with HOST (pinned) buffers: H2D of A,B
           inside the timed region.
 roofline= the DGEMM kernel against the FP64 tensor (DMMA) peak measured on this GPU in this run
           by the library's register-resident probe.
-cpu_baseline / --impl reference = the reference's own trusted C DGEMM (oracle/_ref, ATL_drefgemm,
-          built from /root/reference by oracle/build_ref.sh; falls back to the oracle port) on all
-          host cores, on a bounded column slab of the same workload.
+cpu_baseline / --impl reference = the reference's hand-tuned AVX-512 DGEMM micro-kernel under a threaded access-major
+          driver (oracle/_ref/libatltuned.so, built from /root/reference by oracle/build_ref.sh) on all host cores, on the
+          whole N=16384 problem when the step budget allows; falls back to the reference's triple-loop ATL_drefgemm
+          ("untuned-reference") and then to the oracle port when the tuned kernel cannot run.
 dgetrf  = clapack_dgetrf at the same N on device-resident data (rank 0, N=1 only for now).
 Prints ONE JSON line on rank 0.
 """
